@@ -1,0 +1,194 @@
+"""CPU tests: the oracle against the reference's golden vectors (tests/golden/make_golden.py)."""
+import os
+
+import numpy as np
+import pandas as pd
+import pytest
+import scipy.optimize as sopt
+
+from oracle import gpr, lbfgs, selection
+from oracle.local_expert_oi import run_local_expert_oi
+
+
+def _load(golden_dir, name):
+    return np.load(os.path.join(golden_dir, name))
+
+
+def test_kat1_sklearn_matern32_optimise(golden_dir):
+    """tests/test_localexperts.py:204-227 with the oracle standing in for GPflowGPRModel (tol 1e-6)."""
+    g = _load(golden_dir, "kat1.npz")
+    for optimiser in ("scipy", "own"):
+        m = gpr.OracleGPRModel(coords=g["x_train"].copy(), obs=g["y_train"].copy(), obs_mean=None)
+        m.set_parameters(likelihood_variance=float(g["eps"]) ** 2)
+        m.set_parameter_constraints({"lengthscales": {"low": 1e-10, "high": 5.0}})
+        ok = m.optimise_parameters(fixed_params=["likelihood_variance", "kernel_variance"],
+                                   optimiser=optimiser)
+        out = m.predict(coords=g["x_test"])
+        assert ok
+        assert abs(m.get_lengthscales()[0] - g["ls"]) < 1e-6
+        assert abs(-m.get_objective_function_value() - g["ml"]) < 1e-6
+        assert abs(out["f*"] - g["pred_mean"]) < 1e-6
+        assert abs(out["f*_var"] - g["pred_var"]) < 1e-6
+
+
+def test_kat3_rbf_lml(golden_dir):
+    """docs/notebooks/gp_regression.ipynb: LML 16.6180 at l=1, effective variance sqrt(1.5), noise 0.0025."""
+    g = _load(golden_dir, "kat3.npz")
+    v = gpr.lml(g["x"][:, None], g["y"], np.array([1.0]), float(g["kv"]), float(g["nv"]), "RBF")
+    assert abs(v - 16.6180) < 5e-5
+    assert abs(v - g["ml"]) < 1e-10
+    mean, fvar, _ = gpr.predict(g["x"][:, None], g["y"], g["xs"], np.array([1.0]), float(g["kv"]),
+                                float(g["nv"]), "RBF")
+    np.testing.assert_allclose(mean, g["mean"], rtol=1e-9)
+    np.testing.assert_allclose(fvar, g["var"], rtol=1e-6, atol=1e-12)
+
+
+@pytest.mark.parametrize("tag", ["a", "b", "c"])
+def test_gpr3d_vs_reference_purepython(golden_dir, tag):
+    """3-D ARD Matern-3/2 at fixed hyper-parameters vs the reference's PurePythonGPR (1e-8 rel)."""
+    g = _load(golden_dir, "gpr3d.npz")
+    X, z, Xs = g[f"{tag}_X"], g[f"{tag}_z"], g[f"{tag}_Xs"]
+    m = gpr.OracleGPRModel(coords=X.copy(), obs=z.copy(), coords_scale=[50_000, 50_000, 1],
+                           obs_mean="local", kernel="Matern32",
+                           kernel_kwargs={"lengthscales": g[f"{tag}_ls"], "variance": float(g[f"{tag}_kv"])},
+                           noise_variance=float(g[f"{tag}_nv"]))
+    nl = m.get_objective_function_value()
+    assert abs(nl - g[f"{tag}_nlml"]) <= 1e-8 * abs(g[f"{tag}_nlml"])
+    out = m.predict(Xs)
+    np.testing.assert_allclose(out["f*"], g[f"{tag}_fstar"], rtol=1e-8, atol=1e-12)
+    # PurePythonGPR.predict returns f*_var as (sqrt(var))**2
+    np.testing.assert_allclose(out["f*_var"], g[f"{tag}_fvar"], rtol=1e-8, atol=1e-14)
+    # gpflow matmul-form r^2 differs only at the documented 1e-7 level
+    m2 = gpr.OracleGPRModel(coords=X.copy(), obs=z.copy(), coords_scale=[50_000, 50_000, 1],
+                            obs_mean="local", kernel_kwargs={"lengthscales": g[f"{tag}_ls"],
+                                                             "variance": float(g[f"{tag}_kv"])},
+                            noise_variance=float(g[f"{tag}_nv"]), r2_form="gpflow")
+    assert abs(m2.get_objective_function_value() - nl) <= 1e-6 * abs(nl)
+
+
+def test_gradient_matches_finite_differences():
+    rng = np.random.default_rng(0)
+    X = rng.uniform(0, 6, (120, 3))
+    y = np.sin(X[:, 0]) + 0.1 * rng.standard_normal(120)
+    th = np.array([1.3, 0.7, 2.0, 0.8, 0.05])
+    for kern in ("Matern32", "Matern52", "Matern12", "RBF"):
+        f0, g0 = gpr.neg_lml_and_grad(X, y, th[:3], th[3], th[4], kern)
+        assert abs(f0 + gpr.lml(X, y, th[:3], th[3], th[4], kern)) < 1e-9
+        for i in range(5):
+            h = 1e-6 * th[i]
+            tp, tm = th.copy(), th.copy()
+            tp[i] += h
+            tm[i] -= h
+            gn = (-gpr.lml(X, y, tp[:3], tp[3], tp[4], kern) + gpr.lml(X, y, tm[:3], tm[3], tm[4], kern)) / (2 * h)
+            assert abs(g0[i] - gn) <= 1e-6 * max(1.0, abs(gn))
+
+
+def test_bijectors_roundtrip():
+    u = np.linspace(-30, 30, 61)
+    np.testing.assert_allclose(gpr.softplus_inv(gpr.softplus(u)), u, rtol=1e-9, atol=1e-9)
+    t = gpr.Transform(1, [2e-13, 1e-8], [12.0, 9.0])
+    th = np.array([1.0, 3.0])
+    np.testing.assert_allclose(t.fwd(t.inv(th)), th, rtol=1e-14)
+    # GPSat/tests/test_utils.py:962-1023 pins softplus/sigmoid to 1e-14 / 1e-12 vs TF: known values
+    assert abs(gpr.softplus(np.array([0.0]))[0] - np.log(2.0)) < 1e-15
+    assert abs(gpr.sigmoid(np.array([0.0]))[0] - 0.5) < 1e-16
+
+
+def test_constraints_move_within_tol():
+    """Worked example of SURVEY 8a row M4 (inline config): noise start 0.005625, l unchanged."""
+    X = np.random.default_rng(1).normal(size=(10, 3))
+    m = gpr.OracleGPRModel(coords=X, obs=X[:, 0].copy(), coords_scale=[50_000, 50_000, 1])
+    m.set_parameter_constraints({"lengthscales": {"low": [1e-8] * 3, "high": [600000, 600000, 9], "scale": True},
+                                 "likelihood_variance": {"low": 0.00125, "high": 0.01}},
+                                move_within_tol=True, tol=1e-2)
+    np.testing.assert_array_equal(m.get_lengthscales(), np.ones(3))
+    assert abs(m.get_likelihood_variance() - 0.005625) < 1e-15
+    np.testing.assert_allclose(m.tr["lengthscales"].high, [12.0, 12.0, 9.0])
+
+
+def test_own_lbfgs_reproduces_scipy_trajectory():
+    def ros(x):
+        return sopt.rosen(x), sopt.rosen_der(x)
+    x0 = np.array([-1.2, 1, 0.5, 2, -1])
+    r1 = sopt.minimize(ros, x0, jac=True, method="L-BFGS-B")
+    r2 = lbfgs.minimize_lbfgs(ros, x0)
+    assert (r1.nit, r1.nfev) == (r2["nit"], r2["nfev"])
+    np.testing.assert_allclose(r1.x, r2["x"], rtol=1e-9, atol=1e-12)
+    # GPR objective with the inline-example constraints
+    rng = np.random.default_rng(0)
+    X = rng.uniform(0, 6, (150, 3))
+    y = np.sin(X[:, 0]) + 0.1 * rng.standard_normal(150)
+    res = []
+    for optimiser in ("scipy", "own"):
+        m = gpr.OracleGPRModel(coords=X.copy(), obs=y.copy(), obs_mean="local")
+        m.set_parameter_constraints({"lengthscales": {"low": [1e-8] * 3, "high": [12, 12, 9]},
+                                     "likelihood_variance": {"low": 0.00125, "high": 0.01}},
+                                    move_within_tol=True, tol=1e-2)
+        ok = m.optimise_parameters(optimiser=optimiser)
+        r = m.opt_result
+        res.append((ok, r["nit"], r["nfev"], m.get_objective_function_value()))
+    assert res[0][:3] == res[1][:3]
+    assert abs(res[0][3] - res[1][3]) <= 1e-9 * abs(res[0][3])
+
+
+def test_selection_vs_reference_kdtree(golden_dir):
+    """Bit-exact index sets vs DataLoader.local_data_select run on the real scipy KDTree."""
+    g = _load(golden_dir, "select_3d.npz")
+    cols = {"x": g["x"], "y": g["y"], "t": g["t"]}
+    ls = [{"col": "t", "comp": "<=", "val": 4}, {"col": "t", "comp": ">=", "val": -4},
+          {"col": ["x", "y"], "comp": "<", "val": float(g["radius"])}]
+    off = g["offsets"]
+    for i in range(len(g["ex"])):
+        ref = {"x": g["ex"][i], "y": g["ey"][i], "t": g["et"][i]}
+        idx = selection.local_select_indices(cols, ref, ls)
+        np.testing.assert_array_equal(idx, g["idx"][off[i]:off[i + 1]])
+
+
+def test_predloc_vs_reference_numba(golden_dir):
+    g = _load(golden_dir, "predloc_2d.npz")
+    pc = {"x": g["px"], "y": g["py"]}
+    off = g["offsets"]
+    for i in range(len(g["ex"])):
+        row = {"x": g["ex"][i], "y": g["ey"][i], "t": g["et"][i]}
+        out, idx = selection.prediction_locations(pc, ["x", "y", "t"], row, float(g["max_dist"]))
+        np.testing.assert_array_equal(idx, g["idx"][off[i]:off[i + 1]])
+        if i == 0:
+            np.testing.assert_array_equal(out, g["first"])
+
+
+def test_kat4_selection_counts(golden_dir):
+    """docs/notebooks/1d_local_expert_model_part_2.ipynb: 62, 59 and 41, 37, 44, 38."""
+    g = _load(golden_dir, "kat4.npz")
+    cols = {"x": g["x"]}
+    for r, cs, ns in ((0.15, g["c015"], g["n015"]), (0.1, g["c01"], g["n01"])):
+        ls = [{"col": "x", "comp": "<=", "val": r}, {"col": "x", "comp": ">=", "val": -r}]
+        got = [len(selection.local_select_indices(cols, {"x": c}, ls)) for c in cs]
+        assert got == list(ns)
+    assert list(g["n015"]) == [62, 59] and list(g["n01"]) == [41, 37, 44, 38]
+
+
+def test_loop_oracle_tables():
+    rng = np.random.default_rng(3)
+    n = 3000
+    df = pd.DataFrame({"x": rng.uniform(-5e5, 5e5, n), "y": rng.uniform(-5e5, 5e5, n),
+                       "t": rng.integers(18322, 18331, n).astype(float)})
+    df["z"] = 0.1 * np.sin(df["x"] / 2e5) + rng.normal(0, 0.05, n)
+    eloc = pd.DataFrame({"x": [0.0, 2e5, 9e6], "y": [0.0, -1e5, 9e6], "t": [18326.0] * 3})
+    gx, gy = np.meshgrid(np.arange(-4e5, 4e5 + 1, 5e4), np.arange(-4e5, 4e5 + 1, 5e4))
+    ploc = pd.DataFrame({"x": np.r_[gx.ravel(), 9e6], "y": np.r_[gy.ravel(), 9e6]})
+    data = {"data_source": df, "obs_col": "z", "coords_col": ["x", "y", "t"],
+            "local_select": [{"col": "t", "comp": "<=", "val": 4}, {"col": "t", "comp": ">=", "val": -4},
+                             {"col": ["x", "y"], "comp": "<", "val": 150_000}]}
+    model = {"init_params": {"coords_scale": [50000, 50000, 1]},
+             "constraints": {"lengthscales": {"low": [1e-8] * 3, "high": [600000, 600000, 9]},
+                             "likelihood_variance": {"low": 0.00125, "high": 0.01}}}
+    tables, per = run_local_expert_oi(eloc, data, model,
+                                      {"method": "from_dataframe", "df": ploc, "max_dist": 100_000})
+    assert set(tables) == {"run_details", "preds", "lengthscales", "kernel_variance", "likelihood_variance"}
+    assert list(tables["run_details"].index.names) == ["x", "y", "t"]
+    assert len(tables["run_details"]) == 3  # third expert has too few obs but is recorded
+    assert tables["run_details"]["optimise_success"].tolist()[:2] == [True, True]
+    assert np.isnan(tables["run_details"]["objective_value"].iloc[2])
+    assert list(tables["preds"].columns) == ["_dim_0", "f*", "f*_var", "y_var", "f_bar",
+                                             "pred_loc_x", "pred_loc_y", "pred_loc_t"]
+    assert len(tables["lengthscales"]) == 6
