@@ -1,0 +1,565 @@
+// gpsat_b200: host orchestration + C ABI (see include/gpsat_b200.h).
+#include "../../include/gpsat_b200.h"
+
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <numeric>
+#include <string>
+#include <vector>
+
+#include "engine.cuh"
+#include "selection.cuh"
+
+using namespace gpsat;
+
+static_assert(GPSAT_MAXD == MAXD && GPSAT_MAXP == MAXP, "header / device constants out of sync");
+static_assert(sizeof(gpsat_sel_spec) == sizeof(SelSpec), "selection spec layout mismatch");
+
+static thread_local std::string g_err;
+static int fail(int code, const std::string& msg) {
+  g_err = msg;
+  return code;
+}
+#define CK(call)                                                                          \
+  do {                                                                                    \
+    cudaError_t e__ = (call);                                                             \
+    if (e__ != cudaSuccess)                                                               \
+      return fail((int)e__, std::string(#call) + ": " + cudaGetErrorString(e__));         \
+  } while (0)
+
+struct Buf {
+  void* p = nullptr;
+  size_t cap = 0;
+};
+
+struct gpsat_handle {
+  int device = 0;
+  size_t budget = 0;
+  int n_sm = 148;
+  long long launches = 0;
+  bool profiling = false;
+  double ms[4] = {0, 0, 0, 0};
+  double fl[3] = {0, 0, 0};
+  std::vector<cudaEvent_t> ev;
+  size_t ev_used = 0;
+  std::vector<double> ev_flops;  // N^3/3 summed over active slots for each recorded round
+  Buf Lt, Xt, coords, yobs, ints, theta, logdet, gpart, fout, gout, states, order, pslot, pres, scratch, items;
+  int* host_ints = nullptr;  // pinned
+  size_t host_ints_cap = 0;
+  bool attrs_set = false;
+};
+
+static int ensure(Buf& b, size_t bytes) {
+  if (bytes <= b.cap) return 0;
+  if (b.p) cudaFree(b.p);
+  b.p = nullptr;
+  b.cap = 0;
+  size_t want = bytes + bytes / 8;
+  cudaError_t e = cudaMalloc(&b.p, want);
+  if (e != cudaSuccess) {
+    e = cudaMalloc(&b.p, bytes);
+    want = bytes;
+  }
+  if (e != cudaSuccess) return fail(GPSAT_ENOMEM, "cudaMalloc failed for " + std::to_string(bytes) + " bytes");
+  b.cap = want;
+  return 0;
+}
+#define ENS(buf, bytes)                     \
+  do {                                      \
+    int r__ = ensure(buf, (size_t)(bytes)); \
+    if (r__) return r__;                    \
+  } while (0)
+
+extern "C" const char* gpsat_last_error(void) { return g_err.c_str(); }
+extern "C" int gpsat_version(void) { return 100; }
+
+extern "C" void gpsat_default_opts(gpsat_opt_options* o) {
+  o->maxcor = 10;
+  o->maxiter = 10000;
+  o->maxfun = 15000;
+  o->maxls = 20;
+  o->ftol = 2.220446049250313e-09;
+  o->gtol = 1e-5;
+}
+
+extern "C" int gpsat_create(gpsat_handle** out, int device, size_t mem_budget_bytes) {
+  if (!out) return fail(GPSAT_EINVAL, "out is NULL");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return fail(GPSAT_ENOGPU, "no CUDA device");
+  if (device < 0 || device >= ndev) return fail(GPSAT_EINVAL, "bad device index");
+  CK(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  CK(cudaGetDeviceProperties(&prop, device));
+  if (prop.major < 10)
+    return fail(GPSAT_ENOGPU, std::string("gpsat_b200 is built for sm_100a only; found ") + prop.name);
+  gpsat_handle* h = new gpsat_handle();
+  h->device = device;
+  h->n_sm = prop.multiProcessorCount;
+  size_t free_b = 0, total_b = 0;
+  CK(cudaMemGetInfo(&free_b, &total_b));
+  h->budget = mem_budget_bytes ? mem_budget_bytes : (size_t)(0.7 * (double)free_b);
+  CK(cudaFuncSetAttribute(k_potrf_update, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+  CK(cudaFuncSetAttribute(k_potrf_trsm, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+  CK(cudaFuncSetAttribute(k_trtri_step, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+  CK(cudaFuncSetAttribute(k_lauum_trace, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+  CK(cudaFuncSetAttribute(k_predict, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+  *out = h;
+  return 0;
+}
+
+extern "C" int gpsat_destroy(gpsat_handle* h) {
+  if (!h) return 0;
+  cudaSetDevice(h->device);
+  Buf* bs[] = {&h->Lt, &h->Xt, &h->coords, &h->yobs, &h->ints, &h->theta, &h->logdet, &h->gpart,
+               &h->fout, &h->gout, &h->states, &h->order, &h->pslot, &h->pres, &h->scratch, &h->items};
+  for (Buf* b : bs)
+    if (b->p) cudaFree(b->p);
+  if (h->host_ints) cudaFreeHost(h->host_ints);
+  for (auto e : h->ev) cudaEventDestroy(e);
+  delete h;
+  return 0;
+}
+
+extern "C" long long gpsat_launch_count(const gpsat_handle* h) { return h ? h->launches : 0; }
+extern "C" int gpsat_set_profiling(gpsat_handle* h, int enabled) {
+  if (!h) return GPSAT_EINVAL;
+  h->profiling = enabled != 0;
+  for (int k = 0; k < 4; ++k) h->ms[k] = 0;
+  for (int k = 0; k < 3; ++k) h->fl[k] = 0;
+  return 0;
+}
+extern "C" int gpsat_get_profile(gpsat_handle* h, double* a, double* b, double* c, double* d, double* fa,
+                                 double* fb, double* fc) {
+  if (!h) return GPSAT_EINVAL;
+  *a = h->ms[0]; *b = h->ms[1]; *c = h->ms[2]; *d = h->ms[3];
+  *fa = h->fl[0]; *fb = h->fl[1]; *fc = h->fl[2];
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// slot pool planning and workspace
+// ------------------------------------------------------------------------------------------
+struct Plan {
+  int S, nbmax, npmax, ntmax;
+  std::vector<int> order;  // expert ids, descending n
+};
+
+static size_t slot_bytes(int nbmax) {
+  const size_t ntmax = (size_t)nbmax * (nbmax + 1) / 2;
+  const size_t npmax = (size_t)nbmax * TB;
+  return 2 * ntmax * TILE_BYTES + (MAXD + 1) * npmax * 8 + nbmax * 8 + ntmax * NG * 8 + sizeof(LbfgsState) + 256;
+}
+
+static int make_plan(gpsat_handle* h, const gpsat_batch* b, Plan& pl, size_t extra_per_slot = 0) {
+  const int E = b->n_experts;
+  if (E <= 0) return fail(GPSAT_EINVAL, "n_experts must be positive");
+  if (b->D < 1 || b->D > MAXD) return fail(GPSAT_EINVAL, "D out of range");
+  pl.order.resize(E);
+  std::iota(pl.order.begin(), pl.order.end(), 0);
+  const long long* off = b->offsets_host;
+  std::stable_sort(pl.order.begin(), pl.order.end(),
+                   [&](int x, int y) { return (off[x + 1] - off[x]) > (off[y + 1] - off[y]); });
+  long long nmax = off[pl.order[0] + 1] - off[pl.order[0]];
+  long long nmin = off[pl.order[E - 1] + 1] - off[pl.order[E - 1]];
+  if (nmin < 1) return fail(GPSAT_EINVAL, "every expert needs at least one observation");
+  pl.nbmax = (int)(nmax / TB) + 1;
+  pl.npmax = pl.nbmax * TB;
+  pl.ntmax = pl.nbmax * (pl.nbmax + 1) / 2;
+  const size_t per = slot_bytes(pl.nbmax) + extra_per_slot;
+  long long cap = (long long)(h->budget / per);
+  if (cap < 1) return fail(GPSAT_ENOMEM, "one expert of this size does not fit the memory budget");
+  pl.S = (int)std::min<long long>(std::min<long long>(E, cap), 4LL * h->n_sm);
+  return 0;
+}
+
+struct Work {
+  SlotCtx c;
+  SlotAux a;
+};
+
+static int setup_work(gpsat_handle* h, const gpsat_batch* b, const Plan& pl, Work& w, cudaStream_t st) {
+  const int S = pl.S;
+  ENS(h->Lt, (size_t)S * pl.ntmax * TILE_BYTES);
+  ENS(h->Xt, (size_t)S * pl.ntmax * TILE_BYTES);
+  ENS(h->coords, (size_t)S * MAXD * pl.npmax * 8);
+  ENS(h->yobs, (size_t)S * pl.npmax * 8);
+  ENS(h->ints, (size_t)(6 * S + 8) * sizeof(int));
+  ENS(h->theta, (size_t)S * MAXP * 8);
+  ENS(h->logdet, (size_t)S * pl.nbmax * 8);
+  ENS(h->gpart, (size_t)S * pl.ntmax * NG * 8);
+  ENS(h->fout, (size_t)S * 8);
+  ENS(h->gout, (size_t)S * MAXP * 8);
+  ENS(h->states, (size_t)S * sizeof(LbfgsState));
+  ENS(h->order, (size_t)b->n_experts * sizeof(int));
+  if (h->host_ints_cap < (size_t)(3 * S + 8)) {
+    if (h->host_ints) cudaFreeHost(h->host_ints);
+    CK(cudaMallocHost(&h->host_ints, (size_t)(3 * S + 8) * sizeof(int)));
+    h->host_ints_cap = 3 * S + 8;
+  }
+  int* ip = (int*)h->ints.p;
+  SlotCtx& c = w.c;
+  c.S = S; c.D = b->D; c.kid = b->kernel_id; c.nbmax = pl.nbmax; c.npmax = pl.npmax; c.ntmax = pl.ntmax;
+  c.tile_stride = (long)pl.ntmax * TILE_ELEMS;
+  c.Lt = (double*)h->Lt.p; c.Xt = (double*)h->Xt.p;
+  c.coords = (double*)h->coords.p; c.yobs = (double*)h->yobs.p;
+  c.n = ip; c.nb = ip + S; c.active = ip + 2 * S; c.fail = ip + 3 * S;
+  c.theta = (double*)h->theta.p; c.logdet_part = (double*)h->logdet.p; c.gpart = (double*)h->gpart.p;
+  c.fout = (double*)h->fout.p; c.gout = (double*)h->gout.p;
+  w.a.slot_expert = ip + 4 * S;
+  w.a.queue_head = ip + 5 * S;
+  w.a.states = (LbfgsState*)h->states.p;
+  CK(cudaMemsetAsync(h->ints.p, 0, (size_t)(6 * S + 8) * sizeof(int), st));
+  CK(cudaMemcpyAsync(h->order.p, pl.order.data(), (size_t)b->n_experts * sizeof(int), cudaMemcpyHostToDevice, st));
+  return 0;
+}
+
+static BatchIn make_batch_in(const gpsat_batch* b, const double* theta_dev, const int* order_dev) {
+  BatchIn bi;
+  bi.E = b->n_experts; bi.D = b->D;
+  bi.coords = b->coords_dev; bi.obs = b->obs_dev; bi.offsets = b->offsets_dev;
+  bi.order = order_dev; bi.theta0 = theta_dev;
+  for (int d = 0; d < MAXD; ++d) bi.coords_scale[d] = (d < b->D && b->coords_scale[d] != 0.0) ? b->coords_scale[d] : 1.0;
+  bi.obs_scale = (b->obs_scale != 0.0) ? b->obs_scale : 1.0;
+  bi.obs_mean_local = b->obs_mean_local;
+  bi.obs_mean_out = b->obs_mean_out_dev;
+  return bi;
+}
+
+static cudaEvent_t next_event(gpsat_handle* h) {
+  if (h->ev_used == h->ev.size()) {
+    cudaEvent_t e;
+    cudaEventCreate(&e);
+    h->ev.push_back(e);
+  }
+  return h->ev[h->ev_used++];
+}
+
+// one objective evaluation for all active slots.  nbm: max blocks among active slots.
+static int run_round(gpsat_handle* h, const SlotCtx& c, int nbm, bool inverse, bool grad, cudaStream_t st,
+                     double flops_third) {
+  const bool prof = h->profiling;
+  if (prof) { cudaEventRecord(next_event(h), st); h->ev_flops.push_back(flops_third); }
+  for (int j = 0; j < nbm; ++j) {
+    k_potrf_update<<<dim3(nbm - j, c.S), NTHREADS, SMEM_BYTES, st>>>(c, j);
+    ++h->launches;
+    if (j + 1 < nbm) {
+      k_potrf_trsm<<<dim3(nbm - j - 1, c.S), NTHREADS, SMEM_BYTES, st>>>(c, j);
+      ++h->launches;
+    }
+  }
+  if (prof) cudaEventRecord(next_event(h), st);
+  if (inverse) {
+    for (int sd = 1; sd < nbm; ++sd) {
+      k_trtri_step<<<dim3(nbm - sd, c.S), NTHREADS, SMEM_BYTES, st>>>(c, sd);
+      ++h->launches;
+    }
+  }
+  if (prof) cudaEventRecord(next_event(h), st);
+  if (grad) {
+    k_lauum_trace<<<dim3(nbm * (nbm + 1) / 2, c.S), NTHREADS, SMEM_BYTES, st>>>(c);
+    ++h->launches;
+  }
+  if (prof) cudaEventRecord(next_event(h), st);
+  k_finalize<<<c.S, NTHREADS, 0, st>>>(c, grad ? 1 : 0);
+  ++h->launches;
+  if (prof) cudaEventRecord(next_event(h), st);
+  CK(cudaGetLastError());
+  return 0;
+}
+
+static void harvest_profile(gpsat_handle* h, bool inverse, bool grad) {
+  if (!h->profiling) { h->ev_used = 0; h->ev_flops.clear(); return; }
+  const size_t rounds = h->ev_used / 5;
+  for (size_t r = 0; r < rounds; ++r) {
+    float t[4];
+    for (int k = 0; k < 4; ++k) cudaEventElapsedTime(&t[k], h->ev[5 * r + k], h->ev[5 * r + k + 1]);
+    h->ms[0] += t[0]; h->ms[1] += t[1]; h->ms[2] += t[2]; h->ms[3] += t[3];
+    h->fl[0] += h->ev_flops[r];
+    if (inverse) h->fl[1] += h->ev_flops[r];
+    if (grad) h->fl[2] += h->ev_flops[r];
+  }
+  h->ev_used = 0;
+  h->ev_flops.clear();
+}
+
+static int nb_of(const long long* off, int e) { return (int)((off[e + 1] - off[e]) / TB) + 1; }
+static double cube3(const long long* off, int e) {
+  const double n = (double)(off[e + 1] - off[e]);
+  return n * n * n / 3.0;
+}
+
+static TransformSpec identity_transforms(int D) {
+  TransformSpec tr;
+  memset(&tr, 0, sizeof(tr));
+  tr.np = D + 2;
+  tr.nfree = 0;
+  return tr;
+}
+
+// ------------------------------------------------------------------------------------------
+// evaluation
+// ------------------------------------------------------------------------------------------
+extern "C" int gpsat_gpr_eval(gpsat_handle* h, const gpsat_batch* b, const double* theta_dev, double* f_dev,
+                              double* grad_dev, void* stream) {
+  if (!h || !b || !theta_dev) return fail(GPSAT_EINVAL, "null argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  CK(cudaSetDevice(h->device));
+  Plan pl;
+  int r = make_plan(h, b, pl);
+  if (r) return r;
+  Work w;
+  r = setup_work(h, b, pl, w, st);
+  if (r) return r;
+  BatchIn bi = make_batch_in(b, theta_dev, (const int*)h->order.p);
+  TransformSpec tr = identity_transforms(b->D);
+  const bool grad = grad_dev != nullptr;
+  for (int first = 0; first < b->n_experts; first += pl.S) {
+    const int count = std::min(pl.S, b->n_experts - first);
+    k_slot_init<<<pl.S, NTHREADS, 0, st>>>(w.c, w.a, bi, tr, first, count, 0);
+    ++h->launches;
+    double fl = 0;
+    for (int k = 0; k < count; ++k) fl += cube3(b->offsets_host, pl.order[first + k]);
+    r = run_round(h, w.c, nb_of(b->offsets_host, pl.order[first]), grad, grad, st, fl);
+    if (r) return r;
+    k_eval_scatter<<<(count + 127) / 128, 128, 0, st>>>(w.c, w.a, count, f_dev, grad_dev, b->D + 2);
+    ++h->launches;
+  }
+  CK(cudaStreamSynchronize(st));
+  harvest_profile(h, grad, grad);
+  CK(cudaGetLastError());
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// optimisation
+// ------------------------------------------------------------------------------------------
+extern "C" int gpsat_gpr_optimise(gpsat_handle* h, const gpsat_batch* b, const double* theta0_dev,
+                                  const gpsat_transforms* trs, const gpsat_opt_options* opts,
+                                  double* theta_out_dev, double* fobj_out_dev, int* status_out_dev,
+                                  int* nit_out_dev, int* nfev_out_dev, void* stream) {
+  if (!h || !b || !theta0_dev || !trs || !theta_out_dev || !fobj_out_dev || !status_out_dev || !nit_out_dev ||
+      !nfev_out_dev)
+    return fail(GPSAT_EINVAL, "null argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  CK(cudaSetDevice(h->device));
+  gpsat_opt_options od;
+  gpsat_default_opts(&od);
+  if (opts) od = *opts;
+  if (od.maxcor < 1 || od.maxcor > LB_M) return fail(GPSAT_EINVAL, "maxcor must be in [1, 10]");
+  Plan pl;
+  int r = make_plan(h, b, pl);
+  if (r) return r;
+  Work w;
+  r = setup_work(h, b, pl, w, st);
+  if (r) return r;
+  BatchIn bi = make_batch_in(b, theta0_dev, (const int*)h->order.p);
+  TransformSpec tr;
+  memset(&tr, 0, sizeof(tr));
+  tr.np = b->D + 2;
+  for (int p = 0; p < tr.np; ++p) {
+    tr.kind[p] = trs->kind[p];
+    tr.low[p] = trs->low[p];
+    tr.high[p] = trs->high[p];
+    if (trs->trainable[p]) tr.free_idx[tr.nfree++] = p;
+  }
+  if (tr.nfree == 0) return fail(GPSAT_EINVAL, "no trainable parameters (use gpsat_gpr_eval)");
+  LbfgsOpts lo;
+  lo.m = od.maxcor; lo.maxiter = od.maxiter; lo.maxfun = od.maxfun; lo.maxls = od.maxls;
+  lo.factr = od.ftol / 2.220446049250313e-16;
+  lo.pgtol = od.gtol;
+  OptOut out{theta_out_dev, fobj_out_dev, status_out_dev, nit_out_dev, nfev_out_dev};
+  const int S = pl.S;
+  const int count = std::min(S, b->n_experts);
+  k_slot_init<<<S, NTHREADS, 0, st>>>(w.c, w.a, bi, tr, 0, count, 1);
+  ++h->launches;
+  CK(cudaMemcpyAsync(w.a.queue_head, &count, sizeof(int), cudaMemcpyHostToDevice, st));
+  const long long max_rounds = (long long)(b->n_experts / S + 2) * (od.maxfun + od.maxls + 2);
+  for (long long round = 0; round < max_rounds; ++round) {
+    CK(cudaMemcpyAsync(h->host_ints, w.c.n, (size_t)3 * S * sizeof(int), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    // layout of ints: n[S], nb[S], active[S]
+    int nact = 0, nbm = 0;
+    double fl = 0;
+    for (int s = 0; s < S; ++s) {
+      if (h->host_ints[2 * S + s]) {
+        ++nact;
+        nbm = std::max(nbm, h->host_ints[S + s]);
+        const double n = (double)h->host_ints[s];
+        fl += n * n * n / 3.0;
+      }
+    }
+    if (nact == 0) break;
+    r = run_round(h, w.c, nbm, true, true, st, fl);
+    if (r) return r;
+    k_opt_step<<<S, NTHREADS, 0, st>>>(w.c, w.a, bi, tr, lo, out);
+    ++h->launches;
+    if (h->profiling && h->ev_used > 4000) { CK(cudaStreamSynchronize(st)); harvest_profile(h, true, true); }
+  }
+  CK(cudaStreamSynchronize(st));
+  harvest_profile(h, true, true);
+  CK(cudaGetLastError());
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// prediction
+// ------------------------------------------------------------------------------------------
+extern "C" int gpsat_gpr_predict(gpsat_handle* h, const gpsat_batch* b, const double* theta_dev,
+                                 const long long* poff_host, const long long* poff_dev, const double* pcoords_dev,
+                                 double* fmean_dev, double* fvar_dev, double* yvar_dev, double* fobj_dev,
+                                 void* stream) {
+  if (!h || !b || !theta_dev || !poff_host || !poff_dev || !pcoords_dev || !fmean_dev || !fvar_dev || !yvar_dev)
+    return fail(GPSAT_EINVAL, "null argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  CK(cudaSetDevice(h->device));
+  const int E = b->n_experts;
+  long long pmax = 0;
+  for (int e = 0; e < E; ++e) pmax = std::max(pmax, poff_host[e + 1] - poff_host[e]);
+  const int ppmax = (int)((pmax + TB - 1) / TB) * TB;
+  if (ppmax == 0) return 0;
+  Plan pl;
+  int r = make_plan(h, b, pl, (size_t)(MAXD + 2) * ppmax * 8 + 64);
+  if (r) return r;
+  Work w;
+  r = setup_work(h, b, pl, w, st);
+  if (r) return r;
+  const int S = pl.S;
+  const int grid = h->n_sm;
+  ENS(h->pslot, (size_t)S * MAXD * ppmax * 8 + (size_t)(S + 8) * sizeof(int) + MAXD * 8);
+  ENS(h->pres, (size_t)2 * S * ppmax * 8);
+  ENS(h->scratch, (size_t)grid * pl.nbmax * TILE_BYTES);
+  double* pslot = (double*)h->pslot.p;
+  double* cs_dev = pslot + (size_t)S * MAXD * ppmax;
+  int* np_dev = (int*)(cs_dev + MAXD);
+  BatchIn bi = make_batch_in(b, theta_dev, (const int*)h->order.p);
+  CK(cudaMemcpyAsync(cs_dev, bi.coords_scale, MAXD * 8, cudaMemcpyHostToDevice, st));
+  TransformSpec tr = identity_transforms(b->D);
+  std::vector<int> items;
+  for (int first = 0; first < E; first += S) {
+    const int count = std::min(S, E - first);
+    k_slot_init<<<S, NTHREADS, 0, st>>>(w.c, w.a, bi, tr, first, count, 0);
+    ++h->launches;
+    double fl = 0;
+    for (int k = 0; k < count; ++k) fl += cube3(b->offsets_host, pl.order[first + k]);
+    r = run_round(h, w.c, nb_of(b->offsets_host, pl.order[first]), true, false, st, fl);
+    if (r) return r;
+    k_pred_load<<<S, NTHREADS, 0, st>>>(w.a, count, b->D, pcoords_dev, poff_dev, cs_dev, pslot, np_dev, ppmax);
+    ++h->launches;
+    items.clear();
+    std::vector<int> islot, ipb;
+    for (int s = 0; s < count; ++s) {
+      const int e = pl.order[first + s];
+      const int npb = (int)((poff_host[e + 1] - poff_host[e] + TB - 1) / TB);
+      for (int pb = 0; pb < npb; ++pb) { islot.push_back(s); ipb.push_back(pb); }
+    }
+    const int n_items = (int)islot.size();
+    if (n_items > 0) {
+      ENS(h->items, (size_t)2 * n_items * sizeof(int));
+      int* it_dev = (int*)h->items.p;
+      // pageable copies are staged synchronously by the runtime; vectors can be reused afterwards
+      CK(cudaMemcpyAsync(it_dev, islot.data(), (size_t)n_items * sizeof(int), cudaMemcpyHostToDevice, st));
+      CK(cudaMemcpyAsync(it_dev + n_items, ipb.data(), (size_t)n_items * sizeof(int), cudaMemcpyHostToDevice, st));
+      CK(cudaStreamSynchronize(st));
+      PredCtx p;
+      p.ppmax = ppmax; p.pcoords = pslot; p.np = np_dev;
+      p.item_slot = it_dev; p.item_pb = it_dev + n_items; p.n_items = n_items;
+      p.scratch = (double*)h->scratch.p;
+      p.fmean = (double*)h->pres.p;
+      p.fvar = (double*)h->pres.p + (size_t)S * ppmax;
+      k_predict<<<std::min(grid, n_items), NTHREADS, SMEM_BYTES, st>>>(w.c, p);
+      ++h->launches;
+      k_pred_scatter<<<S, NTHREADS, 0, st>>>(w.c, w.a, count, poff_dev, p.fmean, p.fvar, ppmax, fmean_dev,
+                                             fvar_dev, yvar_dev, fobj_dev);
+      ++h->launches;
+    }
+  }
+  CK(cudaStreamSynchronize(st));
+  harvest_profile(h, true, false);
+  CK(cudaGetLastError());
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// misc entry points
+// ------------------------------------------------------------------------------------------
+extern "C" int gpsat_kernel_matrix(const double* x1_dev, int n1, const double* x2_dev, int n2, int D, int kernel_id,
+                                   const double* theta_dev, int add_noise, double* k_dev, void* stream) {
+  if (!x1_dev || !x2_dev || !theta_dev || !k_dev || D < 1 || D > MAXD) return fail(GPSAT_EINVAL, "bad argument");
+  if (n1 <= 0 || n2 <= 0) return 0;
+  dim3 grid((n2 + 63) / 64, (n1 + 15) / 16), block(64, 4);
+  k_kernel_matrix<<<grid, block, 0, (cudaStream_t)stream>>>(x1_dev, n1, x2_dev, n2, D, kernel_id, theta_dev,
+                                                            add_noise, k_dev);
+  CK(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int gpsat_debug_factor(gpsat_handle* h, const gpsat_batch* b, const double* theta_dev, double* l_dense,
+                                  double* x_dense, void* stream) {
+  if (!h || !b || !theta_dev) return fail(GPSAT_EINVAL, "null argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  gpsat_batch b1 = *b;
+  b1.n_experts = 1;
+  Plan pl;
+  int r = make_plan(h, &b1, pl);
+  if (r) return r;
+  Work w;
+  r = setup_work(h, &b1, pl, w, st);
+  if (r) return r;
+  BatchIn bi = make_batch_in(&b1, theta_dev, nullptr);
+  TransformSpec tr = identity_transforms(b->D);
+  k_slot_init<<<pl.S, NTHREADS, 0, st>>>(w.c, w.a, bi, tr, 0, 1, 0);
+  r = run_round(h, w.c, pl.nbmax, true, false, st, 0.0);
+  if (r) return r;
+  if (l_dense) k_unpack_tiles<<<dim3(pl.nbmax, pl.nbmax), 256, 0, st>>>(w.c.Lt, pl.nbmax, l_dense);
+  if (x_dense) k_unpack_tiles<<<dim3(pl.nbmax, pl.nbmax), 256, 0, st>>>(w.c.Xt, pl.nbmax, x_dense);
+  CK(cudaStreamSynchronize(st));
+  harvest_profile(h, true, false);
+  CK(cudaGetLastError());
+  return 0;
+}
+
+static int select_common(const gpsat_sel_spec* spec, const double* table_dev, long long n, const double* refs_dev,
+                         int nrefcols, int E, int fill, long long* counts, const long long* offsets, int* idx,
+                         void* stream) {
+  if (!spec || !table_dev || !refs_dev || nrefcols < 1 || nrefcols > 16 || spec->nterms < 0 ||
+      spec->nterms > SEL_MAXTERMS)
+    return fail(GPSAT_EINVAL, "bad argument");
+  if (E <= 0) return 0;
+  SelSpec sp;
+  memcpy(&sp, spec, sizeof(sp));
+  k_select<<<E, 256, 0, (cudaStream_t)stream>>>(sp, table_dev, (long)n, refs_dev, nrefcols, fill, counts, offsets,
+                                                idx);
+  CK(cudaGetLastError());
+  return 0;
+}
+extern "C" int gpsat_select_count(const gpsat_sel_spec* spec, const double* table_dev, long long n,
+                                  const double* refs_dev, int nrefcols, int E, long long* counts_dev, void* stream) {
+  if (!counts_dev) return fail(GPSAT_EINVAL, "counts_dev is NULL");
+  return select_common(spec, table_dev, n, refs_dev, nrefcols, E, 0, counts_dev, nullptr, nullptr, stream);
+}
+extern "C" int gpsat_select_fill(const gpsat_sel_spec* spec, const double* table_dev, long long n,
+                                 const double* refs_dev, int nrefcols, int E, const long long* offsets_dev,
+                                 int* idx_dev, void* stream) {
+  if (!offsets_dev || !idx_dev) return fail(GPSAT_EINVAL, "null output");
+  return select_common(spec, table_dev, n, refs_dev, nrefcols, E, 1, nullptr, offsets_dev, idx_dev, stream);
+}
+
+// ---- host-side L-BFGS hooks (same code the device runs) ----
+extern "C" size_t gpsat_lbfgs_state_bytes(void) { return sizeof(LbfgsState); }
+extern "C" void gpsat_lbfgs_init_host(void* state, const double* x0, int n) {
+  lb_init(*reinterpret_cast<LbfgsState*>(state), x0, n);
+}
+extern "C" int gpsat_lbfgs_tell_host(void* state, const gpsat_opt_options* o, double f, const double* g,
+                                     double* x_next, int* nit, int* nfev) {
+  LbfgsState& st = *reinterpret_cast<LbfgsState*>(state);
+  LbfgsOpts lo;
+  lo.m = o->maxcor; lo.maxiter = o->maxiter; lo.maxfun = o->maxfun; lo.maxls = o->maxls;
+  lo.factr = o->ftol / 2.220446049250313e-16;
+  lo.pgtol = o->gtol;
+  lbfgs_tell(st, lo, f, g);
+  for (int i = 0; i < st.n; ++i) x_next[i] = st.x[i];
+  if (nit) *nit = st.nit;
+  if (nfev) *nfev = st.nfev;
+  return st.status;
+}

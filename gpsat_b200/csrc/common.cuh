@@ -1,0 +1,119 @@
+// gpsat_b200: common device primitives (sm_100a).
+//
+// Tile format used by every dense kernel in this library
+// ------------------------------------------------------
+// A symmetric / triangular N x N matrix of one expert is stored as PACKED LOWER-TRIANGULAR
+// 64 x 64 TILES: tile (i, j), j <= i, lives at tile index i*(i+1)/2 + j and is one contiguous
+// 32 KiB blob, so a whole operand tile is one linear bulk copy into shared memory.
+// Inside a tile element (r, c) is stored at   r*64 + (c ^ ((r & 3) << 2))   (doubles).
+// That XOR swizzle makes BOTH DMMA fragment access patterns bank-conflict free straight
+// from the copied image (no padding, no re-layout pass):
+//   row pattern  : lane reads (row0 + lane/4, k0 + lane%4)
+//   col pattern  : lane reads (k0 + lane%4, col0 + lane/4)
+// (a 64-bit shared load is served per half-warp over 16 8-byte banks; in both patterns the
+//  16 lanes of a half-warp hit 16 distinct banks.)
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace gpsat {
+
+constexpr int TB = 64;                 // tile edge
+constexpr int TILE_ELEMS = TB * TB;    // 4096 doubles
+constexpr int TILE_BYTES = TILE_ELEMS * 8;
+constexpr int MAXD = 4;                // max coordinate dimension
+constexpr int MAXP = MAXD + 2;         // lengthscales..., kernel variance, likelihood variance
+constexpr int NTHREADS = 256;          // CTA size of the tile kernels (8 warps: 4 (M) x 2 (N))
+
+enum KernelId { K_MATERN32 = 0, K_MATERN52 = 1, K_MATERN12 = 2, K_RBF = 3 };
+
+__host__ __device__ __forceinline__ int swz(int r, int c) { return r * TB + (c ^ ((r & 3) << 2)); }
+__host__ __device__ __forceinline__ long tri_index(int i, int j) { return (long)i * (i + 1) / 2 + j; }
+
+// ---- cp.async (LDGSTS) 16-byte copies ----
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
+  uint32_t s = (uint32_t)__cvta_generic_to_shared(smem);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gmem));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
+
+// copy one 32 KiB tile global -> shared with all NTHREADS threads (8 x 16 B each)
+__device__ __forceinline__ void load_tile_async(double* smem_tile, const double* gmem_tile) {
+#pragma unroll
+  for (int c = 0; c < TILE_BYTES / 16 / NTHREADS; ++c) {
+    int idx = threadIdx.x + c * NTHREADS;
+    cp_async16(reinterpret_cast<char*>(smem_tile) + idx * 16,
+               reinterpret_cast<const char*>(gmem_tile) + idx * 16);
+  }
+}
+
+// ---- FP64 tensor-core MMA: D(8x8) += A(8x4) * B(4x8) ----
+// A: lane holds A[lane/4][lane%4]; B: lane holds B[lane%4][lane/4]; C: lane holds C[lane/4][2*(lane%4)+{0,1}]
+__device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+               : "+d"(c0), "+d"(c1)
+               : "d"(a), "d"(b));
+}
+
+// ---- warp / block reductions ----
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// deterministic block sum of NV values per thread; result valid in thread 0. red: >= NV*8 doubles
+template <int NV>
+__device__ __forceinline__ void block_sum(double (&v)[NV], double* red) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int k = 0; k < NV; ++k) {
+    double s = warp_sum(v[k]);
+    if (lane == 0) red[k * (NTHREADS / 32) + warp] = s;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int k = 0; k < NV; ++k) {
+      double s = 0.0;
+      for (int w = 0; w < NTHREADS / 32; ++w) s += red[k * (NTHREADS / 32) + w];
+      v[k] = s;
+    }
+  }
+  __syncthreads();
+}
+
+// ---- stationary kernel functions (gpflow.kernels.*) ----
+// k(r2) and h(r2) with dk/dl_d = h * delta_d^2 / l_d^3   (delta in unscaled units)
+__device__ __forceinline__ void kern_eval(int kid, double r2, double var, double& k, double& h) {
+  if (kid == K_RBF) {
+    k = var * exp(-0.5 * r2);
+    h = k;
+    return;
+  }
+  const double r = sqrt(fmax(r2, 1e-36));
+  if (kid == K_MATERN32) {
+    const double s3 = 1.7320508075688772;
+    const double e = exp(-s3 * r);
+    k = var * (1.0 + s3 * r) * e;
+    h = 3.0 * var * e;
+  } else if (kid == K_MATERN52) {
+    const double s5 = 2.23606797749979;
+    const double e = exp(-s5 * r);
+    k = var * (1.0 + s5 * r + (5.0 / 3.0) * (r * r)) * e;
+    h = var * (5.0 / 3.0) * (1.0 + s5 * r) * e;
+  } else {  // Matern12 / Exponential
+    const double e = exp(-r);
+    k = var * e;
+    h = (r2 > 1e-36) ? k / r : 0.0;
+  }
+}
+__device__ __forceinline__ double kern_value(int kid, double r2, double var) {
+  double k, h;
+  kern_eval(kid, r2, var, k, h);
+  return k;
+}
+
+}  // namespace gpsat

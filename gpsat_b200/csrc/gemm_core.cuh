@@ -1,0 +1,111 @@
+// gpsat_b200: 64x64 FP64 tile GEMM core on the DMMA pipe (mma.sync m8n8k4 f64).
+//
+// tcgen05 has no f64 kind, so the FP64 tensor path on sm_100a is warp-level DMMA with
+// register accumulators.  One CTA (8 warps, 4 along M x 2 along N, 16x32 per warp) owns one
+// 64x64 output tile and streams 64x64 operand tiles (32 KiB contiguous blobs, see common.cuh)
+// through a 2-stage cp.async ring in shared memory.  Both operands can be consumed in either
+// orientation straight from the swizzled image:
+//   TA = false : A[m][k] = Atile(m, k)        TA = true : A[m][k] = Atile(k, m)
+//   TBm = false: B[k][n] = Btile(n, k)  (NT)  TBm = true: B[k][n] = Btile(k, n)
+#pragma once
+#include "common.cuh"
+
+namespace gpsat {
+
+struct Acc {
+  double c[2][4][2];  // [mi][ni][pair]  rows 16*wm + 8*mi + q, cols 32*wn + 8*ni + 2*r + {0,1}
+  __device__ __forceinline__ void zero() {
+#pragma unroll
+    for (int i = 0; i < 2; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) c[i][j][0] = c[i][j][1] = 0.0;
+  }
+};
+
+struct FragCoord {
+  int lane, warp, q, r, wm, wn;
+  __device__ __forceinline__ FragCoord() {
+    lane = threadIdx.x & 31;
+    warp = threadIdx.x >> 5;
+    q = lane >> 2;
+    r = lane & 3;
+    wm = warp & 3;
+    wn = warp >> 2;
+  }
+  __device__ __forceinline__ int row(int mi) const { return 16 * wm + 8 * mi + q; }
+  __device__ __forceinline__ int col(int ni) const { return 32 * wn + 8 * ni + 2 * r; }  // and col+1
+};
+
+// acc += op(As) * op(Bs) for one pair of 64x64 tiles resident in shared memory
+template <bool TA, bool TBm>
+__device__ __forceinline__ void mma_tile(Acc& acc, const double* __restrict__ As,
+                                         const double* __restrict__ Bs, const FragCoord& fc) {
+  int abase[2], bbase[4];
+  const int sq = (fc.q & 3) << 2;
+#pragma unroll
+  for (int mi = 0; mi < 2; ++mi) {
+    const int m = 16 * fc.wm + 8 * mi + fc.q;
+    abase[mi] = TA ? (fc.r * TB + (m ^ (fc.r << 2))) : (m * TB + fc.r);
+  }
+#pragma unroll
+  for (int ni = 0; ni < 4; ++ni) {
+    const int n = 32 * fc.wn + 8 * ni + fc.q;
+    bbase[ni] = TBm ? (fc.r * TB + (n ^ (fc.r << 2))) : (n * TB + fc.r);
+  }
+#pragma unroll
+  for (int k0 = 0; k0 < TB; k0 += 4) {
+    double a[2], b[4];
+    const int kx = k0 ^ sq;  // row pattern: (k0 + r) ^ sq == (k0 ^ sq) + r
+#pragma unroll
+    for (int mi = 0; mi < 2; ++mi) a[mi] = TA ? As[abase[mi] + k0 * TB] : As[abase[mi] + kx];
+#pragma unroll
+    for (int ni = 0; ni < 4; ++ni) b[ni] = TBm ? Bs[bbase[ni] + k0 * TB] : Bs[bbase[ni] + kx];
+#pragma unroll
+    for (int mi = 0; mi < 2; ++mi)
+#pragma unroll
+      for (int ni = 0; ni < 4; ++ni) dmma884(acc.c[mi][ni][0], acc.c[mi][ni][1], a[mi], b[ni]);
+  }
+}
+
+// acc += sum_{k = kbeg}^{kend-1} op(A_k) * op(B_k); a_of(k) / b_of(k) give global tile pointers.
+// smem: 4 tiles (2 stages x {A, B}).  Ends with all async copies drained and a __syncthreads().
+template <bool TA, bool TBm, class FA, class FB>
+__device__ __forceinline__ void gemm_pipeline(Acc& acc, double* smem, int kbeg, int kend, FA a_of,
+                                              FB b_of, const FragCoord& fc) {
+  if (kbeg >= kend) return;
+  load_tile_async(smem, a_of(kbeg));
+  load_tile_async(smem + TILE_ELEMS, b_of(kbeg));
+  cp_async_commit();
+  for (int k = kbeg; k < kend; ++k) {
+    const int st = (k - kbeg) & 1;
+    if (k + 1 < kend) {
+      double* nx = smem + (st ^ 1) * 2 * TILE_ELEMS;
+      load_tile_async(nx, a_of(k + 1));
+      load_tile_async(nx + TILE_ELEMS, b_of(k + 1));
+      cp_async_commit();
+      cp_async_wait<1>();
+    } else {
+      cp_async_wait<0>();
+    }
+    __syncthreads();
+    mma_tile<TA, TBm>(acc, smem + st * 2 * TILE_ELEMS, smem + st * 2 * TILE_ELEMS + TILE_ELEMS, fc);
+    __syncthreads();
+  }
+}
+
+// store the accumulator tile to a swizzled 64x64 tile (global or shared), scaled by `scale`
+__device__ __forceinline__ void store_acc_swizzled(double* __restrict__ tile, const Acc& acc,
+                                                   const FragCoord& fc, double scale = 1.0) {
+#pragma unroll
+  for (int mi = 0; mi < 2; ++mi) {
+    const int m = fc.row(mi);
+#pragma unroll
+    for (int ni = 0; ni < 4; ++ni) {
+      const int n = fc.col(ni);
+      double2 v = make_double2(scale * acc.c[mi][ni][0], scale * acc.c[mi][ni][1]);
+      *reinterpret_cast<double2*>(tile + swz(m, n)) = v;
+    }
+  }
+}
+
+}  // namespace gpsat

@@ -1,0 +1,110 @@
+// gpsat_b200: observation / prediction-location selection.
+//
+// Bit-exact restatement of
+//   DataLoader.local_data_select            (GPSat/dataloader.py:2352-2447)
+//   PredictionLocations._max_dist_bool      (GPSat/prediction_locations.py:18-43)
+// as an order-preserving two-pass stream compaction: pass 1 counts matches per expert, pass 2
+// writes the matching row indices in ascending (source) order.  All distance arithmetic uses
+// __dmul_rn / __dadd_rn so no FMA contraction can change a tie on the radius.
+//   type 0: scalar window   x[col] <comp> (ref[col] + val)
+//   type 1: KD-tree ball    sum_j (x_j - ref_j)^2 <= r*r            (inclusive)
+//   type 2: max_dist        every (d_j*d_j) < r*r and sum_j d_j*d_j < r*r   (strict)
+#pragma once
+#include "common.cuh"
+
+namespace gpsat {
+
+constexpr int SEL_MAXTERMS = 8;
+constexpr int SEL_MAXCOL = 4;
+
+struct SelTerm {
+  int type, ncol, comp, pad_;
+  int col[SEL_MAXCOL];   // column index into the observation table
+  int rcol[SEL_MAXCOL];  // column index into the expert (reference) table
+  double val;
+};
+struct SelSpec {
+  int nterms, pad_;
+  SelTerm t[SEL_MAXTERMS];
+};
+
+__device__ __forceinline__ bool sel_cmp(int comp, double a, double b) {
+  switch (comp) {
+    case 0: return a >= b;
+    case 1: return a > b;
+    case 2: return a == b;
+    case 3: return a < b;
+    default: return a <= b;
+  }
+}
+
+// obs: [ncols][n] column-major table; ref: this expert's row [nrefcols]
+__device__ __forceinline__ bool sel_match(const SelSpec& sp, const double* __restrict__ obs, long n, long row,
+                                          const double* ref) {
+  bool ok = true;
+  for (int k = 0; k < sp.nterms && ok; ++k) {
+    const SelTerm& t = sp.t[k];
+    if (t.type == 0) {
+      ok = sel_cmp(t.comp, obs[(long)t.col[0] * n + row], __dadd_rn(ref[t.rcol[0]], t.val));
+    } else {
+      const double r2 = __dmul_rn(t.val, t.val);
+      double d2 = 0.0;
+      for (int j = 0; j < t.ncol; ++j) {
+        const double d = __dadd_rn(obs[(long)t.col[j] * n + row], -ref[t.rcol[j]]);
+        const double dd = __dmul_rn(d, d);
+        if (t.type == 2 && !(dd < r2)) ok = false;
+        d2 = __dadd_rn(d2, dd);
+      }
+      ok = ok && ((t.type == 1) ? (d2 <= r2) : (d2 < r2));
+    }
+  }
+  return ok;
+}
+
+// grid (E), 256 threads.  fill == 0: counts[e] = matches.  fill == 1: idx[offsets[e] ...] = rows.
+__global__ void __launch_bounds__(256) k_select(SelSpec sp, const double* __restrict__ obs, long n,
+                                                const double* __restrict__ refs, int nrefcols, int fill,
+                                                long long* counts, const long long* offsets, int* idx) {
+  __shared__ double ref[16];
+  __shared__ int wsum[8];
+  __shared__ long long base_sh;
+  const int e = blockIdx.x;
+  if (threadIdx.x < nrefcols) ref[threadIdx.x] = refs[(long)e * nrefcols + threadIdx.x];
+  if (threadIdx.x == 0) base_sh = fill ? offsets[e] : 0;
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  long long total = 0;
+  for (long r0 = 0; r0 < n; r0 += 256) {
+    const long row = r0 + threadIdx.x;
+    const bool m = (row < n) && sel_match(sp, obs, n, row, ref);
+    const unsigned bal = __ballot_sync(0xffffffffu, m);
+    if (!fill) {
+      if (lane == 0) total += __popc(bal);
+      continue;
+    }
+    if (lane == 0) wsum[warp] = __popc(bal);
+    __syncthreads();
+    int before = 0, all = 0;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) {
+      const int v = wsum[w];
+      if (w < warp) before += v;
+      all += v;
+    }
+    if (m) idx[base_sh + before + __popc(bal & ((1u << lane) - 1u))] = (int)row;
+    __syncthreads();
+    if (threadIdx.x == 0) base_sh += all;
+  }
+  if (!fill) {
+    // lane-0 partials -> block total
+    if (lane == 0) wsum[warp] = (int)total;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      long long t = 0;
+      for (int w = 0; w < 8; ++w) t += wsum[w];
+      counts[e] = t;
+    }
+  }
+}
+
+}  // namespace gpsat

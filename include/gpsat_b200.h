@@ -1,0 +1,161 @@
+/* gpsat_b200 -- C ABI of the B200-native batched local-expert GPR engine.
+ *
+ * Drop-in boundary for the hot path of CPOMUCL/GPSat (citations relative to the reference tree):
+ * the per-expert loop body of LocalExpertOI.run (GPSat/local_experts.py:930-1260) as reached
+ * through the BaseGPRModel interface (GPSat/models/base_model.py:17-448) and its GPflow
+ * implementation (GPSat/models/gpflow_models.py:26-663).  The reference is pure Python and has
+ * no FFI of its own; the binding a maintainer adds is a ctypes stub.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; all *_dev pointers are CUDA device pointers, everything
+ *     else is host memory.  All arithmetic is IEEE float64.
+ *   - every entry point returns 0 on success, a negative GPSAT_E* code or a positive cudaError_t.
+ *     No C++ exception crosses the boundary.  gpsat_last_error() gives a message.
+ *   - experts are passed CSR style: offsets[E+1] into row-major coords[sumN][D] / obs[sumN].
+ *   - hyper-parameter vectors have stride GPSAT_MAXP: lengthscales[D], kernel_variance,
+ *     likelihood_variance (constrained values, like get_parameters()).
+ *   - work is enqueued on `stream` (a cudaStream_t passed as void*); calls that return results
+ *     to host memory synchronise that stream before returning.
+ */
+#ifndef GPSAT_B200_H
+#define GPSAT_B200_H
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GPSAT_MAXD 4
+#define GPSAT_MAXP 6
+#define GPSAT_SEL_MAXTERMS 8
+
+#define GPSAT_EINVAL (-1)   /* bad argument */
+#define GPSAT_ENOMEM (-2)   /* workspace does not fit the memory budget */
+#define GPSAT_ENOGPU (-3)   /* no CUDA device / wrong architecture */
+
+/* kernel ids: gpflow.kernels.{Matern32, Matern52, Matern12|Exponential, SquaredExponential|RBF}
+ * (gpflow_models.py:116-135) */
+enum { GPSAT_MATERN32 = 0, GPSAT_MATERN52 = 1, GPSAT_MATERN12 = 2, GPSAT_RBF = 3 };
+
+/* L-BFGS termination, mirrors scipy L-BFGS-B messages (gpflow_models.py:317-329):
+ * 1, 2 -> optimise_parameters() returns True; 3, 4, 5 -> False */
+enum { GPSAT_OPT_RUNNING = 0, GPSAT_OPT_CONV_PGTOL = 1, GPSAT_OPT_CONV_FTOL = 2,
+       GPSAT_OPT_MAXITER = 3, GPSAT_OPT_MAXFUN = 4, GPSAT_OPT_ABNORMAL = 5 };
+
+typedef struct gpsat_handle gpsat_handle;
+
+/* One batch of experts resident in device memory.  Replaces the (df_local, coords_col, obs_col,
+ * coords_scale, obs_scale, obs_mean) arguments of BaseGPRModel.__init__ (base_model.py:83-245). */
+typedef struct {
+  int n_experts;
+  int D;                          /* coordinate dimension, <= GPSAT_MAXD */
+  int kernel_id;
+  int obs_mean_local;             /* 1 <=> obs_mean="local" (base_model.py:195-198) */
+  const long long* offsets_host;  /* [E+1] */
+  const long long* offsets_dev;   /* [E+1] */
+  const double* coords_dev;       /* [sumN][D] raw coordinates */
+  const double* obs_dev;          /* [sumN] */
+  double coords_scale[GPSAT_MAXD];
+  double obs_scale;
+  double* obs_mean_out_dev;       /* [E] or NULL: the mean that was subtracted (-> "f_bar") */
+} gpsat_batch;
+
+/* Parameter transforms: gpflow defaults (softplus; likelihood variance softplus + 1e-6) or the
+ * tfp Sigmoid(low, high) installed by set_*_constraints (gpflow_models.py:416-494,592-628). */
+typedef struct {
+  int kind[GPSAT_MAXP];      /* 0: softplus + low, 1: sigmoid(low, high) */
+  double low[GPSAT_MAXP];
+  double high[GPSAT_MAXP];
+  int trainable[GPSAT_MAXP]; /* 0 <=> listed in fixed_params (gpflow_models.py:275-288) */
+} gpsat_transforms;
+
+/* scipy L-BFGS-B options as used by gpflow.optimizers.Scipy (defaults in gpsat_default_opts) */
+typedef struct {
+  int maxcor, maxiter, maxfun, maxls;
+  double ftol, gtol;
+} gpsat_opt_options;
+
+/* local_select / max_dist predicate list (dataloader.py:2405-2444; prediction_locations.py:18-43)
+ * type 0: table[col[0]] <comp> ref[rcol[0]] + val ; comp: 0 >=, 1 >, 2 ==, 3 <, 4 <=
+ * type 1: sum_j (table[col[j]] - ref[rcol[j]])^2 <= val*val      (KDTree.query_ball_point)
+ * type 2: strict per-dimension and squared-L2 test against val   (_max_dist_bool) */
+typedef struct {
+  int type, ncol, comp, pad_;
+  int col[4];
+  int rcol[4];
+  double val;
+} gpsat_sel_term;
+typedef struct {
+  int nterms, pad_;
+  gpsat_sel_term t[GPSAT_SEL_MAXTERMS];
+} gpsat_sel_spec;
+
+const char* gpsat_last_error(void);
+int gpsat_version(void);
+
+/* lifetime: owns cached device workspaces; mem_budget_bytes = 0 -> 70% of free device memory */
+int gpsat_create(gpsat_handle** out, int device, size_t mem_budget_bytes);
+int gpsat_destroy(gpsat_handle* h);
+void gpsat_default_opts(gpsat_opt_options* o);
+
+/* S2 / S3: two calls.  counts_dev[E] <- matches; then (after an exclusive scan by the caller)
+ * idx_dev[offsets_dev[e] ...] <- matching row indices in ascending order.
+ * table_dev: [ncols][n] column-major; refs_dev: [E][nrefcols] row-major. */
+int gpsat_select_count(const gpsat_sel_spec* spec, const double* table_dev, long long n,
+                       const double* refs_dev, int nrefcols, int n_experts,
+                       long long* counts_dev, void* stream);
+int gpsat_select_fill(const gpsat_sel_spec* spec, const double* table_dev, long long n,
+                      const double* refs_dev, int nrefcols, int n_experts,
+                      const long long* offsets_dev, int* idx_dev, void* stream);
+
+/* K1: dense kernel matrix K(X1, X2) [n1][n2] row-major (+ likelihood variance on the diagonal
+ * when add_noise); coordinates are raw, divided by coords_scale inside. theta_dev[GPSAT_MAXP]. */
+int gpsat_kernel_matrix(const double* x1_dev, int n1, const double* x2_dev, int n2, int D,
+                        int kernel_id, const double* theta_dev, int add_noise, double* k_dev,
+                        void* stream);
+
+/* L1 + G1: -LML (get_objective_function_value, gpflow_models.py:334-337) and, when
+ * grad_dev != NULL, d(-LML)/d(theta) for every expert at theta_dev[E][GPSAT_MAXP].
+ * fail_dev[E] (optional) is 1 where the Cholesky met a non-positive pivot (f = +inf). */
+int gpsat_gpr_eval(gpsat_handle* h, const gpsat_batch* b, const double* theta_dev,
+                   double* f_dev, double* grad_dev, void* stream);
+
+/* P1: optimise_parameters for every expert (gpflow_models.py:290-329).
+ * theta0_dev: start values after set_parameter_constraints' move_within_tol (host logic).
+ * Outputs per expert: optimised theta, final -LML, termination status, iterations, evaluations. */
+int gpsat_gpr_optimise(gpsat_handle* h, const gpsat_batch* b, const double* theta0_dev,
+                       const gpsat_transforms* tr, const gpsat_opt_options* opts,
+                       double* theta_out_dev, double* fobj_out_dev, int* status_out_dev,
+                       int* nit_out_dev, int* nfev_out_dev, void* stream);
+
+/* F1: predict (gpflow_models.py:186-273) at pred_coords[sumP][D] (raw, CSR by pred_offsets):
+ * f* (fmean), f*_var (fvar), y_var = f*_var + likelihood variance; fobj_dev (optional) gets -LML
+ * at theta (the value run() stores as objective_value, local_experts.py:1135). */
+int gpsat_gpr_predict(gpsat_handle* h, const gpsat_batch* b, const double* theta_dev,
+                      const long long* pred_offsets_host, const long long* pred_offsets_dev,
+                      const double* pred_coords_dev, double* fmean_dev, double* fvar_dev,
+                      double* yvar_dev, double* fobj_dev, void* stream);
+
+/* test hook: dense lower factor L and its inverse X (both (nb*64)^2 row-major, nb = n/64+1, of
+ * the augmented matrix) of expert 0 of the batch at theta_dev. */
+int gpsat_debug_factor(gpsat_handle* h, const gpsat_batch* b, const double* theta_dev,
+                       double* l_dense_dev, double* x_dense_dev, void* stream);
+
+/* counters: kernels launched by this library since the handle was created (bench: gpu_launches),
+ * and CUDA-event time spent in the three DMMA factorisation phases when profiling is enabled */
+long long gpsat_launch_count(const gpsat_handle* h);
+int gpsat_set_profiling(gpsat_handle* h, int enabled);
+int gpsat_get_profile(gpsat_handle* h, double* ms_potrf, double* ms_trtri, double* ms_lauum,
+                      double* ms_other, double* flops_potrf, double* flops_trtri, double* flops_lauum);
+
+/* host-side (CPU) entry to the SAME L-BFGS state machine the device runs, for CPU unit tests of
+ * the optimiser logic against scipy (no GPU needed). */
+size_t gpsat_lbfgs_state_bytes(void);
+void gpsat_lbfgs_init_host(void* state, const double* x0, int n);
+int gpsat_lbfgs_tell_host(void* state, const gpsat_opt_options* o, double f, const double* g,
+                          double* x_next, int* nit, int* nfev);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GPSAT_B200_H */
