@@ -1,0 +1,220 @@
+"""Batched dispatch of the local-expert loop body (the hot path) onto the CUDA engine.
+
+One call processes a whole list of experts that share a global observation table:
+  S3  prediction-location filter   PredictionLocations (GPSat/prediction_locations.py:18-43,208-273)
+  S2  observation selection        DataLoader.local_data_select (GPSat/dataloader.py:2352-2447)
+  O2  skip rules                   GPSat/local_experts.py:962-965, 988-1012
+  M1..M4, P1, L1, F1               model construction, constraints, optimise, objective, predict
+                                   (GPSat/local_experts.py:1043-1159 -> GPSat/models/gpflow_models.py)
+Everything numerical runs in libgpsat_b200.so; torch is used for device buffers and copies only.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass, field
+from typing import Optional, Sequence
+
+import numpy as np
+import torch
+
+from .engine import Engine, make_sel_spec
+from .params import HyperParams, PARAM_NAMES
+
+_SCALAR_COMPS = (">=", ">", "==", "<", "<=")
+
+
+@dataclass
+class ModelSpec:
+    """What LocalExpertOI hands every per-expert model: init_params, constraints, optim_kwargs."""
+    kernel: str = "Matern32"
+    coords_scale: Optional[Sequence[float]] = None
+    obs_scale: float = 1.0
+    obs_mean: Optional[str] = None           # only 'local' is honoured (base_model.py:195-200)
+    lengthscales: Optional[Sequence[float]] = None
+    kernel_variance: float = 1.0
+    likelihood_variance: float = 1.0          # gpflow default when noise_variance is None
+    constraints: Optional[dict] = None
+    fixed_params: Sequence[str] = field(default_factory=list)
+    max_iter: int = 10_000
+    opt_kwargs: dict = field(default_factory=dict)   # ftol / gtol / maxcor / maxls / maxfun overrides
+
+    @staticmethod
+    def from_model_config(model_config: dict) -> "ModelSpec":
+        """Translate a reference model config (init_params / constraints / optim_kwargs)."""
+        ip = dict(model_config.get("init_params") or {})
+        kk = dict(ip.pop("kernel_kwargs", None) or {})
+        ok = dict(model_config.get("optim_kwargs") or {})
+        spec = ModelSpec(kernel=ip.pop("kernel", "Matern32"), coords_scale=ip.pop("coords_scale", None),
+                         obs_scale=ip.pop("obs_scale", None) or 1.0, obs_mean=ip.pop("obs_mean", None),
+                         lengthscales=kk.pop("lengthscales", None), kernel_variance=kk.pop("variance", 1.0),
+                         constraints=model_config.get("constraints"),
+                         fixed_params=list(ok.pop("fixed_params", None) or []),
+                         max_iter=int(ok.pop("max_iter", 10_000)), opt_kwargs=ok)
+        nv = ip.pop("noise_variance", None)
+        if nv is not None:
+            spec.likelihood_variance = float(nv)
+        assert ip.pop("mean_function", None) is None, "mean functions are not supported by the batched engine"
+        ip.pop("verbose", None)
+        assert not kk and not ip, f"unsupported init_params for the batched engine: {list(ip) + list(kk)}"
+        return spec
+
+    def hyper_params(self, D) -> HyperParams:
+        """Start values and bijectors after set_parameter_constraints(..., move_within_tol=True, tol=1e-2)
+        exactly as LocalExpertOI.run applies them (local_experts.py:1110-1115)."""
+        hp = HyperParams(D, self.lengthscales, self.kernel_variance, self.likelihood_variance)
+        cs = None if self.coords_scale is None else np.atleast_2d(np.asarray(self.coords_scale, dtype=np.float64))
+        for name, c in (self.constraints or {}).items():
+            c = dict(c)
+            if cs is not None and name == "lengthscales":
+                c["scale"] = True
+            hp.set_constraints(name, coords_scale=cs, move_within_tol=c.pop("move_within_tol", True),
+                               tol=c.pop("tol", 1e-2), **c)
+        return hp
+
+
+def sel_terms(local_select, table_cols, ref_cols):
+    """local_select (reference format) -> gpsat_sel_spec terms, in listed order."""
+    terms = []
+    for ls in local_select:
+        col, comp = ls["col"], ls["comp"]
+        if isinstance(col, str):
+            assert comp in _SCALAR_COMPS, f"comp '{comp}' is not valid"
+            terms.append({"type": 0, "cols": [table_cols.index(col)], "rcols": [ref_cols.index(col)],
+                          "comp": comp, "val": ls["val"]})
+        else:
+            assert comp in ("<", "<="), f"for multi dimensional values only less than comparison handled"
+            terms.append({"type": 1, "cols": [table_cols.index(c) for c in col],
+                          "rcols": [ref_cols.index(c) for c in col], "val": ls["val"]})
+    return terms
+
+
+def run_experts(eng: Engine, spec: ModelSpec, table_dev: torch.Tensor, table_cols, obs_col, coords_col,
+                refs_dev: torch.Tensor, ref_cols, local_select, pred_table_dev=None, pred_cols=None,
+                max_dist=None, optimise=True, predict=True, min_obs=3, theta_init=None):
+    """Run the loop body for every row of refs_dev.  All inputs / outputs are device tensors.
+
+    table_dev [ncols, n] (column-major observation table), refs_dev [E, nref] expert rows,
+    pred_table_dev [npc, n_pred] (None: predict at the expert location).
+    theta_init [E, D+2]: per-expert start values (load_params); constraints' move_within_tol is
+    applied to them like the reference does after loading (local_experts.py:1086-1115).
+    """
+    dev = eng.device
+    D = len(coords_col)
+    E = refs_dev.shape[0]
+    assert all(c in ref_cols for c in coords_col), "expert locations must hold every coords_col"
+    # ---- S3: prediction locations ----
+    if pred_table_dev is not None:
+        found = [c for c in coords_col if c in pred_cols]
+        if max_dist is not None:
+            pspec = make_sel_spec([{"type": 2, "cols": [pred_cols.index(c) for c in found],
+                                    "rcols": [ref_cols.index(c) for c in found], "val": max_dist}])
+        else:
+            pspec = make_sel_spec([])
+        pcounts = eng.select_count(pspec, pred_table_dev, refs_dev)
+    else:
+        pcounts = torch.ones(E, dtype=torch.int64, device=dev)
+    # ---- S2: observation selection ----
+    ospec = make_sel_spec(sel_terms(local_select, list(table_cols), list(ref_cols)))
+    ocounts = eng.select_count(ospec, table_dev, refs_dev)
+    has_pred = pcounts > 0                         # local_experts.py:962-965: skipped silently
+    too_few = has_pred & (ocounts < min_obs)       # local_experts.py:988-1012: recorded, not run
+    valid = has_pred & ~too_few
+    vidx = torch.nonzero(valid).squeeze(1)
+    out = {"num_obs": ocounts, "has_pred": has_pred, "too_few": too_few, "valid": valid, "valid_idx": vidx}
+    Ev = int(vidx.numel())
+    out["n_valid"] = Ev
+    if Ev == 0:
+        return out
+    refs_v = refs_dev.index_select(0, vidx).contiguous()
+    ooff = torch.zeros(Ev + 1, dtype=torch.int64, device=dev)
+    ooff[1:] = torch.cumsum(ocounts.index_select(0, vidx), 0)
+    poff = torch.zeros(Ev + 1, dtype=torch.int64, device=dev)
+    poff[1:] = torch.cumsum(pcounts.index_select(0, vidx), 0)
+    offs_host = torch.stack([ooff, poff]).cpu().numpy()      # one D2H sync for both CSR arrays
+    ooff_h, poff_h = np.ascontiguousarray(offs_host[0]), np.ascontiguousarray(offs_host[1])
+    oidx = eng.select_fill(ospec, table_dev, refs_v, ooff, int(ooff_h[-1]))
+    coords, obs = eng.gather_rows(table_dev, oidx, [table_cols.index(c) for c in coords_col],
+                                  table_cols.index(obs_col))
+    cs = 1.0 if spec.coords_scale is None else spec.coords_scale
+    batch = eng.make_batch_dev(ooff_h, ooff, coords, obs, kernel=spec.kernel, coords_scale=cs,
+                               obs_scale=spec.obs_scale, obs_mean_local=(spec.obs_mean == "local"))
+    out.update(obs_offsets=ooff, obs_idx=oidx, obs_mean=batch.obs_mean_dev)
+    # ---- M2..M4: start values + bijectors ----
+    hp = spec.hyper_params(D)
+    kind, low, high = hp.transforms()
+    if theta_init is None:
+        theta0 = hp.theta()
+    else:
+        th = torch.as_tensor(theta_init, dtype=torch.float64, device=dev).index_select(0, vidx)
+        theta0 = _move_within_tol(th, spec, hp)
+    # ---- P1 ----
+    if optimise:
+        ok = dict(spec.opt_kwargs)
+        res = eng.optimise(batch, theta0, kind, low, high, hp.trainable_mask(spec.fixed_params),
+                           maxiter=spec.max_iter, **ok)
+        theta = res["theta_full"]
+        out.update(status=res["status"], nit=res["nit"], nfev=res["nfev"])
+    else:
+        theta = eng._theta_dev(theta0, Ev, D)
+    out["theta"] = theta[:, :D + 2]
+    # ---- F1 (+ L1: objective at the final parameters, local_experts.py:1135) ----
+    if predict:
+        if pred_table_dev is not None:
+            pidx = eng.select_fill(pspec, pred_table_dev, refs_v, poff, int(poff_h[-1]))
+            pcoords = eng.gather_pred(pred_table_dev, refs_v, poff, pidx,
+                                      [pred_cols.index(c) if c in pred_cols else -1 for c in coords_col],
+                                      [ref_cols.index(c) for c in coords_col])
+            out["pred_idx"] = pidx
+        else:
+            pcoords = refs_v[:, [ref_cols.index(c) for c in coords_col]].contiguous()
+        fm, fv, yv, fo = eng.predict(batch, theta, poff_h, pcoords, pred_offsets_dev=poff)
+        out.update(pred_offsets=poff, pred_coords=pcoords, fmean=fm, fvar=fv, yvar=yv, fobj=fo)
+    else:
+        fo, _ = eng.eval(batch, theta, grad=False)
+        out["fobj"] = fo
+    return out
+
+
+def _move_within_tol(theta: torch.Tensor, spec: ModelSpec, hp: HyperParams) -> torch.Tensor:
+    """Vectorised move_within_tol over per-expert loaded parameters (gpflow_models.py:471-486)."""
+    th = theta.clone()
+    D = hp.D
+    sl = {"lengthscales": slice(0, D), "kernel_variance": slice(D, D + 1), "likelihood_variance": slice(D + 1, D + 2)}
+    for name, c in (spec.constraints or {}).items():
+        if not c.get("move_within_tol", True):
+            continue
+        _, low, high = hp.tr[name]
+        tol = min(c.get("tol", 1e-2), float(np.min(high - low)) / 2)
+        lo = torch.as_tensor(low + tol, dtype=torch.float64, device=th.device)
+        hi = torch.as_tensor(high - tol, dtype=torch.float64, device=th.device)
+        v = th[:, sl[name]]
+        v = torch.where(v > hi, hi.expand_as(v), v)
+        v = torch.where(v < lo, lo.expand_as(v), v)
+        th[:, sl[name]] = v
+    return th
+
+
+def run_experts_host(eng: Engine, spec: ModelSpec, table, table_cols, obs_col, coords_col, experts, ref_cols,
+                     local_select, pred_table=None, pred_cols=None, max_dist=None, optimise=True, predict=True,
+                     min_obs=3, theta_init=None):
+    """Host-buffer entry: numpy / (pinned) CPU tensors in, numpy out.  This is the call the
+    LocalExpertOI-compatible driver makes; its cost includes every host<->device copy."""
+    dev = eng.device
+
+    def up(x):
+        if x is None:
+            return None
+        t = x if isinstance(x, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(x, dtype=np.float64))
+        return t.to(dev, non_blocking=True)
+
+    res = run_experts(eng, spec, up(table), table_cols, obs_col, coords_col, up(experts), ref_cols, local_select,
+                      pred_table_dev=up(pred_table), pred_cols=pred_cols, max_dist=max_dist, optimise=optimise,
+                      predict=predict, min_obs=min_obs, theta_init=theta_init)
+    out = {}
+    for k, v in res.items():
+        out[k] = v.cpu().numpy() if isinstance(v, torch.Tensor) else v
+    return out
+
+
+def h2d_bytes(*arrays):
+    return int(sum(0 if a is None else (a.numel() * a.element_size() if isinstance(a, torch.Tensor) else a.nbytes)
+                   for a in arrays))

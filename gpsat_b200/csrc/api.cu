@@ -545,6 +545,88 @@ extern "C" int gpsat_select_fill(const gpsat_sel_spec* spec, const double* table
   return select_common(spec, table_dev, n, refs_dev, nrefcols, E, 1, nullptr, offsets_dev, idx_dev, stream);
 }
 
+extern "C" int gpsat_gather_rows(const double* table_dev, long long n, const int* idx_dev, long long total,
+                                 int D, const int* coord_cols, int obs_col, double* coords_dev, double* obs_dev,
+                                 void* stream) {
+  if (!table_dev || !coords_dev || !coord_cols || D < 1 || D > MAXD) return fail(GPSAT_EINVAL, "bad argument");
+  if (total <= 0) return 0;
+  if (!idx_dev) return fail(GPSAT_EINVAL, "idx_dev is NULL");
+  GatherCols gc;
+  gc.D = D;
+  gc.ocol = obs_col;
+  for (int d = 0; d < MAXD; ++d) gc.ccols[d] = d < D ? coord_cols[d] : 0;
+  const int grid = (int)std::min<long long>((total + 255) / 256, 148LL * 16);
+  k_gather_rows<<<grid, 256, 0, (cudaStream_t)stream>>>(gc, table_dev, (long)n, idx_dev, (long)total, coords_dev,
+                                                        obs_col >= 0 ? obs_dev : nullptr);
+  CK(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int gpsat_gather_pred(const double* table_dev, long long n, const double* refs_dev, int nrefcols,
+                                 int n_experts, const long long* offsets_dev, const int* idx_dev, int D,
+                                 const int* table_cols, const int* ref_cols, double* out_dev, void* stream) {
+  if (!table_dev || !refs_dev || !offsets_dev || !out_dev || !table_cols || !ref_cols || D < 1 || D > MAXD)
+    return fail(GPSAT_EINVAL, "bad argument");
+  if (n_experts <= 0) return 0;
+  PredCols pc;
+  pc.D = D;
+  for (int d = 0; d < MAXD; ++d) {
+    pc.tcol[d] = d < D ? table_cols[d] : -1;
+    pc.rcol[d] = d < D ? ref_cols[d] : 0;
+  }
+  k_gather_pred<<<n_experts, 256, 0, (cudaStream_t)stream>>>(pc, table_dev, (long)n, refs_dev, nrefcols,
+                                                             offsets_dev, idx_dev, out_dev);
+  CK(cudaGetLastError());
+  return 0;
+}
+
+// ---- FP64 tensor-pipe speed of light: register-resident DMMA chains, no memory traffic ----
+__global__ void __launch_bounds__(256) k_dmma_peak(int iters, double* sink) {
+  double c[8][2];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) c[k][0] = c[k][1] = 0.0;
+  double a = 1.0 + threadIdx.x * 1e-9, b = 1.0 - threadIdx.x * 1e-9;
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int k = 0; k < 8; ++k) dmma884(c[k][0], c[k][1], a, b);
+  }
+  double s = 0.0;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) s += c[k][0] + c[k][1];
+  if (s == 12345.678) sink[0] = s;
+}
+extern "C" int gpsat_dmma_peak(int device, int iters, double* tflops_out, double* ms_out) {
+  if (!tflops_out || iters < 1) return fail(GPSAT_EINVAL, "bad argument");
+  CK(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  CK(cudaGetDeviceProperties(&prop, device));
+  double* sink = nullptr;
+  CK(cudaMalloc(&sink, 8));
+  const int grid = prop.multiProcessorCount * 4;   // 4 x 8 warps per SM
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0);
+  cudaEventCreate(&e1);
+  k_dmma_peak<<<grid, 256>>>(iters / 8 + 1, sink);  // warm-up
+  double best = 1e30;
+  for (int rep = 0; rep < 5; ++rep) {
+    cudaEventRecord(e0);
+    k_dmma_peak<<<grid, 256>>>(iters, sink);
+    cudaEventRecord(e1);
+    CK(cudaEventSynchronize(e1));
+    float ms = 0;
+    cudaEventElapsedTime(&ms, e0, e1);
+    best = std::min(best, (double)ms);
+  }
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  cudaFree(sink);
+  const double flops = 2.0 * 8 * 8 * 4 * 8.0 * (double)iters * (256 / 32) * (double)grid;
+  *tflops_out = flops / (best * 1e-3) / 1e12;
+  if (ms_out) *ms_out = best;
+  CK(cudaGetLastError());
+  return 0;
+}
+
 // ---- host-side L-BFGS hooks (same code the device runs) ----
 extern "C" size_t gpsat_lbfgs_state_bytes(void) { return sizeof(LbfgsState); }
 extern "C" void gpsat_lbfgs_init_host(void* state, const double* x0, int n) {

@@ -107,4 +107,41 @@ __global__ void __launch_bounds__(256) k_select(SelSpec sp, const double* __rest
   }
 }
 
+// gather selected rows of a column-major table into the CSR batch layout the GPR entry points
+// take: coords[total][D] row-major (from columns ccols[0..D-1]) and obs[total] (column ocol).
+struct GatherCols {
+  int D, ocol;
+  int ccols[MAXD];
+};
+__global__ void __launch_bounds__(256) k_gather_rows(GatherCols gc, const double* __restrict__ table, long n,
+                                                     const int* __restrict__ idx, long total,
+                                                     double* __restrict__ coords, double* __restrict__ obs) {
+  for (long t = blockIdx.x * (long)blockDim.x + threadIdx.x; t < total; t += (long)gridDim.x * blockDim.x) {
+    const long row = idx[t];
+    for (int d = 0; d < gc.D; ++d) coords[t * gc.D + d] = table[(long)gc.ccols[d] * n + row];
+    if (obs) obs[t] = table[(long)gc.ocol * n + row];
+  }
+}
+
+// prediction coordinates of every expert: selected rows of the prediction-location table for the
+// columns it has (tcol[d] >= 0), the expert's own value for the others (tcol[d] < 0 -> refs[e][rcol[d]])
+// (PredictionLocations._from_dataframe, prediction_locations.py:258-271).  grid (E)
+struct PredCols {
+  int D;
+  int tcol[MAXD];
+  int rcol[MAXD];
+};
+__global__ void __launch_bounds__(256) k_gather_pred(PredCols pc, const double* __restrict__ table, long n,
+                                                     const double* __restrict__ refs, int nrefcols,
+                                                     const long long* __restrict__ offsets,
+                                                     const int* __restrict__ idx, double* __restrict__ out) {
+  const int e = blockIdx.x;
+  const long long o0 = offsets[e], o1 = offsets[e + 1];
+  for (long long t = o0 + threadIdx.x; t < o1; t += blockDim.x) {
+    const long row = idx[t];
+    for (int d = 0; d < pc.D; ++d)
+      out[t * pc.D + d] = (pc.tcol[d] >= 0) ? table[(long)pc.tcol[d] * n + row] : refs[(long)e * nrefcols + pc.rcol[d]];
+  }
+}
+
 }  // namespace gpsat

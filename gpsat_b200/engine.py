@@ -111,6 +111,15 @@ class Engine:
                            coords_scale=coords_scale, obs_scale=obs_scale, obs_mean_local=obs_mean_local,
                            obs_mean_dev=torch.zeros(E, dtype=torch.float64, device=self.device))
 
+    def make_batch_dev(self, offsets_host, offsets_dev, coords_dev, obs_dev, kernel="Matern32", coords_scale=1.0,
+                       obs_scale=1.0, obs_mean_local=False) -> ExpertBatch:
+        """Batch over buffers that already live on the device (no copies)."""
+        E = len(offsets_host) - 1
+        return ExpertBatch(offsets_host=np.ascontiguousarray(offsets_host, dtype=np.int64), offsets_dev=offsets_dev,
+                           coords_dev=coords_dev, obs_dev=obs_dev, D=coords_dev.shape[1], kernel=kernel,
+                           coords_scale=coords_scale, obs_scale=obs_scale, obs_mean_local=obs_mean_local,
+                           obs_mean_dev=torch.zeros(E, dtype=torch.float64, device=self.device))
+
     def _theta_dev(self, theta, E, D):
         th = torch.as_tensor(np.asarray(theta, dtype=np.float64)) if not isinstance(theta, torch.Tensor) else theta
         th = th.to(self.device, dtype=torch.float64)
@@ -156,14 +165,16 @@ class Engine:
                 "nfev": nfev}
 
     # ---- F1 ----
-    def predict(self, batch: ExpertBatch, theta, pred_offsets, pred_coords):
+    def predict(self, batch: ExpertBatch, theta, pred_offsets, pred_coords, pred_offsets_dev=None):
         E, D = batch.n_experts, batch.D
         th = self._theta_dev(theta, E, D)
         poff_host = np.ascontiguousarray(np.asarray(pred_offsets, dtype=np.int64))
         assert len(poff_host) == E + 1
-        poff_dev = torch.as_tensor(poff_host).to(self.device)
+        poff_dev = torch.as_tensor(poff_host).to(self.device) if pred_offsets_dev is None else pred_offsets_dev
         if isinstance(pred_coords, torch.Tensor):
             pc = pred_coords.to(self.device, dtype=torch.float64).contiguous()
+            if pc.ndim == 1:
+                pc = pc[:, None].contiguous()
         else:
             pc = torch.as_tensor(np.ascontiguousarray(pred_coords, dtype=np.float64)).to(self.device)
         P = int(poff_host[-1])
@@ -208,25 +219,62 @@ class Engine:
         return L, X
 
     # ---- S2 / S3 ----
-    def select(self, spec: "_lib.SelSpec", table_dev: torch.Tensor, refs_dev: torch.Tensor):
-        """table_dev: [ncols, n] float64 column-major table; refs_dev: [E, nrefcols].
-        Returns (offsets int64 [E+1], idx int32 [total]) on the device; indices ascending per expert."""
+    def select_count(self, spec: "_lib.SelSpec", table_dev: torch.Tensor, refs_dev: torch.Tensor):
+        """matches per expert (int64 [E]); table_dev [ncols, n] column-major, refs_dev [E, nrefcols]."""
         assert table_dev.is_contiguous() and refs_dev.is_contiguous()
-        n = table_dev.shape[1]
         E, nref = refs_dev.shape
         counts = torch.zeros(E, dtype=torch.int64, device=self.device)
-        st = _stream_ptr(self.device)
-        _lib.check(self.lib.gpsat_select_count(C.byref(spec), _ptr(table_dev), n, _ptr(refs_dev), nref, E,
-                                               _ptr(counts), st))
-        offsets = torch.zeros(E + 1, dtype=torch.int64, device=self.device)
+        _lib.check(self.lib.gpsat_select_count(C.byref(spec), _ptr(table_dev), table_dev.shape[1], _ptr(refs_dev),
+                                               nref, E, _ptr(counts), _stream_ptr(self.device)))
+        return counts
+
+    def select_fill(self, spec: "_lib.SelSpec", table_dev: torch.Tensor, refs_dev: torch.Tensor,
+                    offsets: torch.Tensor, total: int):
+        """matching row indices (int32 [total]) in ascending order per expert at offsets[e]."""
+        assert table_dev.is_contiguous() and refs_dev.is_contiguous()
+        E, nref = refs_dev.shape
+        idx = torch.empty(max(total, 1), dtype=torch.int32, device=self.device)
+        _lib.check(self.lib.gpsat_select_fill(C.byref(spec), _ptr(table_dev), table_dev.shape[1], _ptr(refs_dev),
+                                              nref, E, _ptr(offsets), _ptr(idx), _stream_ptr(self.device)))
+        return idx[:total]
+
+    def select(self, spec: "_lib.SelSpec", table_dev: torch.Tensor, refs_dev: torch.Tensor):
+        """Returns (offsets int64 [E+1], idx int32 [total]) on the device; indices ascending per expert."""
+        counts = self.select_count(spec, table_dev, refs_dev)
+        offsets = torch.zeros(refs_dev.shape[0] + 1, dtype=torch.int64, device=self.device)
         offsets[1:] = torch.cumsum(counts, 0)
         total = int(offsets[-1].item())
-        idx = torch.empty(max(total, 1), dtype=torch.int32, device=self.device)
-        _lib.check(self.lib.gpsat_select_fill(C.byref(spec), _ptr(table_dev), n, _ptr(refs_dev), nref, E,
-                                              _ptr(offsets), _ptr(idx), st))
-        return offsets, idx[:total]
+        return offsets, self.select_fill(spec, table_dev, refs_dev, offsets, total)
+
+    def gather_rows(self, table_dev: torch.Tensor, idx: torch.Tensor, coord_cols, obs_col):
+        """coords [total, D] (row-major) and obs [total] of the selected rows of a [ncols, n] table."""
+        total, D = int(idx.numel()), len(coord_cols)
+        coords = torch.empty(total, D, dtype=torch.float64, device=self.device)
+        obs = torch.empty(total, dtype=torch.float64, device=self.device)
+        cc = (C.c_int * D)(*[int(c) for c in coord_cols])
+        _lib.check(self.lib.gpsat_gather_rows(_ptr(table_dev), table_dev.shape[1], _ptr(idx), total, D, cc,
+                                              int(obs_col), _ptr(coords), _ptr(obs), _stream_ptr(self.device)))
+        return coords, obs
+
+    def gather_pred(self, table_dev: torch.Tensor, refs_dev: torch.Tensor, offsets: torch.Tensor,
+                    idx: torch.Tensor, table_cols, ref_cols):
+        """Prediction coords [total, D]: table column table_cols[d] (>= 0) or the expert's refs[:, ref_cols[d]]."""
+        total, D = int(idx.numel()), len(table_cols)
+        out = torch.empty(total, D, dtype=torch.float64, device=self.device)
+        tc = (C.c_int * D)(*[int(c) for c in table_cols])
+        rc = (C.c_int * D)(*[int(c) for c in ref_cols])
+        _lib.check(self.lib.gpsat_gather_pred(_ptr(table_dev), table_dev.shape[1], _ptr(refs_dev),
+                                              refs_dev.shape[1], refs_dev.shape[0], _ptr(offsets), _ptr(idx), D,
+                                              tc, rc, _ptr(out), _stream_ptr(self.device)))
+        return out
 
     # ---- counters ----
+    def dmma_peak_tflops(self, iters=20000):
+        """FP64 DMMA issue-rate speed of light of this GPU (TFLOP/s), see gpsat_dmma_peak."""
+        tf, ms = C.c_double(), C.c_double()
+        _lib.check(self.lib.gpsat_dmma_peak(self.device.index, iters, C.byref(tf), C.byref(ms)))
+        return tf.value
+
     def launch_count(self):
         return int(self.lib.gpsat_launch_count(self.h))
 

@@ -108,6 +108,20 @@ int gpsat_select_fill(const gpsat_sel_spec* spec, const double* table_dev, long 
                       const double* refs_dev, int nrefcols, int n_experts,
                       const long long* offsets_dev, int* idx_dev, void* stream);
 
+/* pack the selected rows into the CSR batch layout: coords_dev[total][D] <- table columns
+ * coord_cols[0..D-1]; obs_dev[total] <- column obs_col (obs_col < 0: skipped).  Replaces
+ * df.loc[select, :] + data[coords_col].values / data[obs_col].values
+ * (dataloader.py:2447; base_model.py:148-149). */
+int gpsat_gather_rows(const double* table_dev, long long n, const int* idx_dev, long long total, int D,
+                      const int* coord_cols, int obs_col, double* coords_dev, double* obs_dev, void* stream);
+
+/* prediction coordinates out_dev[total][D] of every expert: column table_cols[d] of the selected
+ * prediction-location rows, or (table_cols[d] < 0) the expert's own refs[e][ref_cols[d]]
+ * (PredictionLocations._from_dataframe, prediction_locations.py:258-271). */
+int gpsat_gather_pred(const double* table_dev, long long n, const double* refs_dev, int nrefcols,
+                      int n_experts, const long long* offsets_dev, const int* idx_dev, int D,
+                      const int* table_cols, const int* ref_cols, double* out_dev, void* stream);
+
 /* K1: dense kernel matrix K(X1, X2) [n1][n2] row-major (+ likelihood variance on the diagonal
  * when add_noise); coordinates are raw, divided by coords_scale inside. theta_dev[GPSAT_MAXP]. */
 int gpsat_kernel_matrix(const double* x1_dev, int n1, const double* x2_dev, int n2, int D,
@@ -147,6 +161,10 @@ long long gpsat_launch_count(const gpsat_handle* h);
 int gpsat_set_profiling(gpsat_handle* h, int enabled);
 int gpsat_get_profile(gpsat_handle* h, double* ms_potrf, double* ms_trtri, double* ms_lauum,
                       double* ms_other, double* flops_potrf, double* flops_trtri, double* flops_lauum);
+
+/* roofline denominator for the factorisation kernels: FP64 mma.sync (DMMA m8n8k4) issue rate of
+ * this GPU measured with register-resident accumulator chains (no memory traffic). */
+int gpsat_dmma_peak(int device, int iters, double* tflops_out, double* ms_out);
 
 /* host-side (CPU) entry to the SAME L-BFGS state machine the device runs, for CPU unit tests of
  * the optimiser logic against scipy (no GPU needed). */

@@ -1,0 +1,329 @@
+"""GPU parity tests: the CUDA path (through the C ABI, via gpsat_b200.engine) against the CPU
+oracle and the committed golden vectors.  Tolerances are BASELINE.json's:
+  * fixed hyper-parameters: K, LML, predictive mean / variance within 1e-8 relative
+  * optimised runs: LML >= reference optimum - 1e-6*|LML|; predictions within 1e-4 relative
+  * selection: bit-exact index sets
+"""
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+torch = pytest.importorskip("torch")
+
+from oracle import gpr, selection  # noqa: E402  (test infrastructure: the checker)
+
+RTOL_FIXED = 1e-8
+KERNELS = ["Matern32", "Matern52", "Matern12", "RBF"]
+
+
+@pytest.fixture(scope="module")
+def eng():
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    from gpsat_b200 import build, get_engine
+    build.build()
+    return get_engine(0)
+
+
+def _load(golden_dir, name):
+    return np.load(os.path.join(golden_dir, name))
+
+
+def _synth(rng, n, D=3, scale=True):
+    """GPSat-like local data: 50 km lattice + jitter, integer days, smooth field + noise."""
+    if D == 3:
+        xy = rng.integers(-6, 7, (n, 2)) * 50_000.0 + rng.normal(0, 5_000, (n, 2))
+        t = rng.integers(18322, 18331, n).astype(np.float64)
+        X = np.column_stack([xy, t])
+        z = 0.1 * np.sin(X[:, 0] / 2e5) + 0.05 * np.cos(X[:, 1] / 1.5e5) + rng.normal(0, 0.05, n)
+        cs = np.array([50_000.0, 50_000.0, 1.0])
+    else:
+        X = rng.uniform(0, 6, (n, D))
+        z = np.sin(X[:, 0]) + 0.1 * rng.standard_normal(n)
+        cs = np.ones(D)
+    return X, z, cs
+
+
+def _pack(list_of_X, list_of_z):
+    off = np.zeros(len(list_of_X) + 1, dtype=np.int64)
+    off[1:] = np.cumsum([len(x) for x in list_of_X])
+    return off, np.concatenate(list_of_X, axis=0), np.concatenate(list_of_z)
+
+
+# ---------------------------------------------------------------------------------------------
+# K1
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("kernel", KERNELS)
+def test_kernel_matrix(eng, kernel):
+    rng = np.random.default_rng(11)
+    X, _, cs = _synth(rng, 333)
+    X2, _, _ = _synth(rng, 77)
+    th = np.array([5.18, 3.22, 9.0, 0.015, 0.0033])
+    K = eng.kernel_matrix(X, X2, th, kernel=kernel, coords_scale=cs).cpu().numpy()
+    Kref = gpr.kernel_matrix(X / cs, X2 / cs, th[:3], th[3], kernel)
+    np.testing.assert_allclose(K, Kref, rtol=RTOL_FIXED, atol=1e-300)
+    Ky = eng.kernel_matrix(X, X, th, kernel=kernel, coords_scale=cs, add_noise=True).cpu().numpy()
+    Kyref = gpr.kernel_matrix(X / cs, None, th[:3], th[3], kernel)
+    Kyref[np.diag_indices(len(X))] += th[4]
+    np.testing.assert_allclose(Ky, Kyref, rtol=RTOL_FIXED, atol=1e-300)
+
+
+# ---------------------------------------------------------------------------------------------
+# factor (test hook): L_aug and its inverse
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("n", [5, 64, 130, 257])
+def test_factor_and_inverse(eng, n):
+    rng = np.random.default_rng(n)
+    X, z, cs = _synth(rng, n)
+    th = np.array([2.0, 1.5, 4.0, 0.05, 0.01])
+    off, Xc, zc = _pack([X], [z])
+    b = eng.make_batch(off, Xc, zc, coords_scale=cs)
+    L, Xi = eng.debug_factor(b, th)
+    L, Xi = L.cpu().numpy(), Xi.cpu().numpy()
+    K = gpr.kernel_matrix(X / cs, None, th[:3], th[3], "Matern32")
+    K[np.diag_indices(n)] += th[4]
+    Lref = np.linalg.cholesky(K)
+    np.testing.assert_allclose(L[:n, :n], Lref, rtol=1e-9, atol=1e-12)
+    a = np.linalg.solve(Lref, z)
+    np.testing.assert_allclose(L[n, :n], a, rtol=1e-8, atol=1e-11)
+    npad = L.shape[0]
+    np.testing.assert_allclose(Xi @ L, np.eye(npad), atol=1e-8)
+
+
+# ---------------------------------------------------------------------------------------------
+# L1 + G1
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("kernel", KERNELS)
+def test_objective_and_gradient_ragged_batch(eng, kernel):
+    rng = np.random.default_rng(5)
+    sizes = [1, 2, 63, 64, 65, 127, 128, 129, 200, 400, 31, 513]
+    Xs, zs = [], []
+    for n in sizes:
+        X, z, cs = _synth(rng, n)
+        Xs.append(X)
+        zs.append(z)
+    off, Xc, zc = _pack(Xs, zs)
+    E = len(sizes)
+    theta = np.column_stack([rng.uniform(1.0, 6.0, E), rng.uniform(1.0, 6.0, E), rng.uniform(2.0, 9.0, E),
+                             rng.uniform(0.01, 0.1, E), rng.uniform(0.002, 0.01, E)])
+    b = eng.make_batch(off, Xc, zc, kernel=kernel, coords_scale=cs, obs_mean_local=True)
+    f, g = eng.eval(b, theta, grad=True)
+    f, g = f.cpu().numpy(), g.cpu().numpy()
+    f_only, _ = eng.eval(b, theta, grad=False)
+    for e, n in enumerate(sizes):
+        y = zs[e] - zs[e].mean()
+        fr, gr = gpr.neg_lml_and_grad(Xs[e] / cs, y, theta[e, :3], theta[e, 3], theta[e, 4], kernel)
+        assert abs(f[e] - fr) <= RTOL_FIXED * abs(fr), (n, f[e], fr)
+        np.testing.assert_allclose(g[e], gr, rtol=1e-7, atol=1e-7 * np.abs(gr).max(), err_msg=f"n={n}")
+        assert abs(f_only[e].item() - fr) <= RTOL_FIXED * abs(fr)
+    np.testing.assert_allclose(b.obs_mean_dev.cpu().numpy(), [z.mean() for z in zs], rtol=1e-13)
+
+
+@pytest.mark.parametrize("tag", ["a", "b", "c"])
+def test_golden_gpr3d_fixed_hyperparameters(eng, golden_dir, tag):
+    """Golden vectors produced by the reference's PurePythonGPR (tests/golden/make_golden.py)."""
+    g = _load(golden_dir, "gpr3d.npz")
+    X, z, Xs = g[f"{tag}_X"], g[f"{tag}_z"], g[f"{tag}_Xs"]
+    th = np.concatenate([g[f"{tag}_ls"], [float(g[f"{tag}_kv"])], [float(g[f"{tag}_nv"])]])
+    cs = [50_000.0, 50_000.0, 1.0]
+    off, Xc, zc = _pack([X], [z])
+    b = eng.make_batch(off, Xc, zc, coords_scale=cs, obs_mean_local=True)
+    f, _ = eng.eval(b, th, grad=False)
+    nl = float(g[f"{tag}_nlml"])
+    assert abs(f.item() - nl) <= RTOL_FIXED * abs(nl)
+    fm, fv, yv, fo = eng.predict(b, th, np.array([0, len(Xs)]), Xs)
+    np.testing.assert_allclose(fm.cpu().numpy(), g[f"{tag}_fstar"], rtol=RTOL_FIXED, atol=1e-12)
+    np.testing.assert_allclose(fv.cpu().numpy(), g[f"{tag}_fvar"], rtol=RTOL_FIXED, atol=1e-12)
+    np.testing.assert_allclose(yv.cpu().numpy(), g[f"{tag}_fvar"] + th[4], rtol=RTOL_FIXED, atol=1e-12)
+    assert abs(fo.item() - nl) <= RTOL_FIXED * abs(nl)
+
+
+def test_kat3_rbf(eng, golden_dir):
+    g = _load(golden_dir, "kat3.npz")
+    off, Xc, zc = _pack([g["x"][:, None]], [g["y"]])
+    b = eng.make_batch(off, Xc, zc, kernel="RBF")
+    th = np.array([1.0, float(g["kv"]), float(g["nv"])])
+    f, _ = eng.eval(b, th, grad=False)
+    assert abs(-f.item() - 16.6180) < 5e-5
+    assert abs(-f.item() - float(g["ml"])) <= 1e-8 * abs(float(g["ml"]))
+    fm, fv, _, _ = eng.predict(b, th, np.array([0, 2]), g["xs"])
+    np.testing.assert_allclose(fm.cpu().numpy(), g["mean"], rtol=1e-8)
+    np.testing.assert_allclose(fv.cpu().numpy(), g["var"], rtol=1e-6, atol=1e-12)
+
+
+# ---------------------------------------------------------------------------------------------
+# F1
+# ---------------------------------------------------------------------------------------------
+def test_predict_ragged(eng):
+    rng = np.random.default_rng(17)
+    sizes = [(3, 1), (70, 200), (128, 64), (300, 65), (450, 1), (64, 130)]
+    Xs, zs, Ps = [], [], []
+    for n, p in sizes:
+        X, z, cs = _synth(rng, n)
+        Xs.append(X)
+        zs.append(z)
+        Ps.append(np.column_stack([rng.uniform(-3e5, 3e5, (p, 2)), np.full(p, 18326.0)]))
+    off, Xc, zc = _pack(Xs, zs)
+    poff = np.zeros(len(sizes) + 1, dtype=np.int64)
+    poff[1:] = np.cumsum([p for _, p in sizes])
+    E = len(sizes)
+    theta = np.column_stack([rng.uniform(1.0, 6.0, E), rng.uniform(1.0, 6.0, E), rng.uniform(2.0, 9.0, E),
+                             rng.uniform(0.01, 0.1, E), rng.uniform(0.002, 0.01, E)])
+    b = eng.make_batch(off, Xc, zc, coords_scale=cs, obs_mean_local=True)
+    fm, fv, yv, fo = eng.predict(b, theta, poff, np.concatenate(Ps))
+    fm, fv, yv, fo = fm.cpu().numpy(), fv.cpu().numpy(), yv.cpu().numpy(), fo.cpu().numpy()
+    for e in range(E):
+        y = zs[e] - zs[e].mean()
+        m, v, yvr = gpr.predict(Xs[e] / cs, y, Ps[e] / cs, theta[e, :3], theta[e, 3], theta[e, 4])
+        sl = slice(poff[e], poff[e + 1])
+        np.testing.assert_allclose(fm[sl], m, rtol=RTOL_FIXED, atol=1e-12)
+        np.testing.assert_allclose(fv[sl], v, rtol=RTOL_FIXED, atol=1e-12)
+        np.testing.assert_allclose(yv[sl], yvr, rtol=RTOL_FIXED, atol=1e-12)
+        fr = -gpr.lml(Xs[e] / cs, y, theta[e, :3], theta[e, 3], theta[e, 4])
+        assert abs(fo[e] - fr) <= RTOL_FIXED * abs(fr)
+
+
+# ---------------------------------------------------------------------------------------------
+# P1
+# ---------------------------------------------------------------------------------------------
+def _oracle_model(X, z, cs, kernel="Matern32"):
+    m = gpr.OracleGPRModel(coords=X.copy(), obs=z.copy(), coords_scale=list(cs), obs_mean="local", kernel=kernel)
+    m.set_parameter_constraints({"lengthscales": {"low": [1e-8] * 3, "high": [600000, 600000, 9], "scale": True},
+                                 "likelihood_variance": {"low": 0.00125, "high": 0.01}},
+                                move_within_tol=True, tol=1e-2)
+    return m
+
+
+def test_optimise_matches_reference_optimum(eng):
+    """Inline-example configuration (examples/inline_example.py:326-355) on synthetic local data."""
+    rng = np.random.default_rng(23)
+    sizes = [150, 90, 260, 64, 200, 333, 10, 129]
+    Xs, zs, models = [], [], []
+    for n in sizes:
+        X, z, cs = _synth(rng, n)
+        Xs.append(X)
+        zs.append(z)
+        models.append(_oracle_model(X, z, cs))
+    off, Xc, zc = _pack(Xs, zs)
+    b = eng.make_batch(off, Xc, zc, coords_scale=cs, obs_mean_local=True)
+    m0 = models[0]
+    theta0 = np.concatenate([m0.get_lengthscales(), [m0.get_kernel_variance()], [m0.get_likelihood_variance()]])
+    kind, low, high = m0._transforms_flat()
+    res = eng.optimise(b, theta0, kind, low, high, trainable=[1] * 5)
+    theta = res["theta"].cpu().numpy()
+    fobj = res["fobj"].cpu().numpy()
+    status = res["status"].cpu().numpy()
+    P = 40
+    Xp = np.column_stack([rng.uniform(-3e5, 3e5, (P, 2)), np.full(P, 18326.0)])
+    poff = np.arange(len(sizes) + 1, dtype=np.int64) * P
+    fm, fv, _, fo = eng.predict(b, theta, poff, np.tile(Xp, (len(sizes), 1)))
+    fm, fv, fo = fm.cpu().numpy(), fv.cpu().numpy(), fo.cpu().numpy()
+    for e, m in enumerate(models):
+        ok = m.optimise_parameters()
+        fref = m.get_objective_function_value()
+        # LML >= reference optimum - 1e-6 |LML|   (f = -LML)
+        assert fobj[e] <= fref + 1e-6 * abs(fref), (e, fobj[e], fref)
+        assert abs(fo[e] - fobj[e]) <= 1e-9 * abs(fobj[e])
+        assert (status[e] in (1, 2)) == ok
+        out = m.predict(Xp)
+        sl = slice(poff[e], poff[e + 1])
+        np.testing.assert_allclose(fm[sl], out["f*"], rtol=1e-4, atol=1e-4 * np.abs(out["f*"]).max())
+        np.testing.assert_allclose(fv[sl], out["f*_var"], rtol=1e-4, atol=1e-4 * np.abs(out["f*_var"]).max())
+
+
+def test_kat1_optimised_lengthscale(eng, golden_dir):
+    """tests/test_localexperts.py:204-227: optimised l, LML, f*, f*_var equal sklearn's to 1e-6."""
+    g = _load(golden_dir, "kat1.npz")
+    off, Xc, zc = _pack([g["x_train"]], [g["y_train"][:, 0]])
+    b = eng.make_batch(off, Xc, zc, kernel="Matern32")
+    nv = float(g["eps"]) ** 2
+    res = eng.optimise(b, np.array([1.0, 1.0, nv]), kind=[1, 0, 0], low=[1e-10, 0.0, 1e-6], high=[5.0, 0.0, 0.0],
+                       trainable=[1, 0, 0])
+    th = res["theta"].cpu().numpy()[0]
+    assert int(res["status"][0]) in (1, 2)
+    assert abs(th[0] - float(g["ls"])) < 1e-6
+    assert abs(-float(res["fobj"][0]) - float(g["ml"])) < 1e-6
+    fm, fv, _, _ = eng.predict(b, th, np.array([0, 1]), g["x_test"])
+    assert abs(fm.item() - float(g["pred_mean"][0])) < 1e-6
+    assert abs(fv.item() - float(g["pred_var"][0])) < 1e-6
+
+
+def test_optimise_more_experts_than_slots(eng):
+    """Slot refill path: a tiny memory budget forces experts to stream through few slots."""
+    from gpsat_b200.engine import Engine
+    rng = np.random.default_rng(3)
+    sizes = list(rng.integers(20, 140, 24))
+    Xs, zs = [], []
+    for n in sizes:
+        X, z, cs = _synth(rng, int(n))
+        Xs.append(X)
+        zs.append(z)
+    off, Xc, zc = _pack(Xs, zs)
+    m0 = _oracle_model(Xs[0], zs[0], cs)
+    theta0 = np.concatenate([m0.get_lengthscales(), [m0.get_kernel_variance()], [m0.get_likelihood_variance()]])
+    kind, low, high = m0._transforms_flat()
+    b = eng.make_batch(off, Xc, zc, coords_scale=cs, obs_mean_local=True)
+    full = eng.optimise(b, theta0, kind, low, high, trainable=[1] * 5)
+    small = Engine(0, mem_budget_bytes=5 * 300_000)   # ~5 slots of 3 blocks
+    try:
+        b2 = small.make_batch(off, Xc, zc, coords_scale=cs, obs_mean_local=True)
+        part = small.optimise(b2, theta0, kind, low, high, trainable=[1] * 5)
+        for k in ("theta", "fobj", "status", "nit", "nfev"):
+            np.testing.assert_array_equal(full[k].cpu().numpy(), part[k].cpu().numpy())
+    finally:
+        small.close()
+
+
+# ---------------------------------------------------------------------------------------------
+# S2 / S3
+# ---------------------------------------------------------------------------------------------
+def test_selection_bit_exact(eng, golden_dir):
+    from gpsat_b200.engine import make_sel_spec
+    g = _load(golden_dir, "select_3d.npz")
+    table = torch.as_tensor(np.stack([g["x"], g["y"], g["t"]])).cuda().contiguous()
+    refs = torch.as_tensor(np.column_stack([g["ex"], g["ey"], g["et"]])).cuda().contiguous()
+    spec = make_sel_spec([{"type": 0, "cols": [2], "rcols": [2], "comp": "<=", "val": float(g["t_hi"])},
+                          {"type": 0, "cols": [2], "rcols": [2], "comp": ">=", "val": float(g["t_lo"])},
+                          {"type": 1, "cols": [0, 1], "rcols": [0, 1], "val": float(g["radius"])}])
+    off, idx = eng.select(spec, table, refs)
+    np.testing.assert_array_equal(off.cpu().numpy(), g["offsets"])
+    np.testing.assert_array_equal(idx.cpu().numpy().astype(np.int64), g["idx"])
+
+
+def test_prediction_location_filter_bit_exact(eng, golden_dir):
+    from gpsat_b200.engine import make_sel_spec
+    g = _load(golden_dir, "predloc_2d.npz")
+    table = torch.as_tensor(np.stack([g["px"], g["py"]])).cuda().contiguous()
+    refs = torch.as_tensor(np.column_stack([g["ex"], g["ey"], g["et"]])).cuda().contiguous()
+    spec = make_sel_spec([{"type": 2, "cols": [0, 1], "rcols": [0, 1], "val": float(g["max_dist"])}])
+    off, idx = eng.select(spec, table, refs)
+    np.testing.assert_array_equal(off.cpu().numpy(), g["offsets"])
+    np.testing.assert_array_equal(idx.cpu().numpy().astype(np.int64), g["idx"])
+
+
+def test_selection_large_random_vs_oracle(eng):
+    from gpsat_b200.engine import make_sel_spec
+    rng = np.random.default_rng(99)
+    n, E = 200_000, 64
+    x = rng.integers(-60, 61, n) * 50_000.0
+    y = rng.integers(-60, 61, n) * 50_000.0
+    t = rng.integers(18316, 18337, n).astype(np.float64)
+    ex = rng.integers(-50, 51, E) * 50_000.0
+    ey = rng.integers(-50, 51, E) * 50_000.0
+    et = rng.integers(18320, 18333, E).astype(np.float64)
+    table = torch.as_tensor(np.stack([x, y, t])).cuda().contiguous()
+    refs = torch.as_tensor(np.column_stack([ex, ey, et])).cuda().contiguous()
+    spec = make_sel_spec([{"type": 0, "cols": [2], "rcols": [2], "comp": "<=", "val": 4.0},
+                          {"type": 0, "cols": [2], "rcols": [2], "comp": ">=", "val": -4.0},
+                          {"type": 1, "cols": [0, 1], "rcols": [0, 1], "val": 300_000.0}])
+    off, idx = eng.select(spec, table, refs)
+    off, idx = off.cpu().numpy(), idx.cpu().numpy()
+    cols = {"x": x, "y": y, "t": t}
+    ls = [{"col": "t", "comp": "<=", "val": 4}, {"col": "t", "comp": ">=", "val": -4},
+          {"col": ["x", "y"], "comp": "<", "val": 300_000.0}]
+    for e in range(E):
+        ref = selection.local_select_indices(cols, {"x": ex[e], "y": ey[e], "t": et[e]}, ls)
+        np.testing.assert_array_equal(idx[off[e]:off[e + 1]], ref)
