@@ -78,6 +78,7 @@ _EXPORTS = {
     "gpsat_set_profiling": (C.c_int, [C.c_void_p, C.c_int]),
     "gpsat_get_profile": (C.c_int, [C.c_void_p] + [C.POINTER(C.c_double)] * 7),
     "gpsat_dmma_peak": (C.c_int, [C.c_int, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
+    "gpsat_microbench": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_double)]),
     "gpsat_lbfgs_state_bytes": (C.c_size_t, []),
     "gpsat_lbfgs_init_host": (None, [C.c_void_p, C.c_void_p, C.c_int]),
     "gpsat_lbfgs_tell_host": (C.c_int, [C.c_void_p, C.POINTER(OptOptions), C.c_double, C.c_void_p, C.c_void_p,

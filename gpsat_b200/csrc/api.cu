@@ -10,6 +10,7 @@
 
 #include "engine.cuh"
 #include "selection.cuh"
+#include "microbench.cuh"
 
 using namespace gpsat;
 
@@ -625,6 +626,80 @@ extern "C" int gpsat_dmma_peak(int device, int iters, double* tflops_out, double
   if (ms_out) *ms_out = best;
   CK(cudaGetLastError());
   return 0;
+}
+
+// ---- micro-benchmarks (see microbench.cuh): which = 0..3 chains(1,2,4,8 accumulators) with `param` CTAs
+// per SM; 10/11 = 64x64 / 128x128 core, param = mode (0 smem, 1 HBM stream, 2 L2 shared), nk k-tiles ----
+template <class F>
+static int time_launch(F launch, double* ms_out) {
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0);
+  cudaEventCreate(&e1);
+  launch();
+  double best = 1e30;
+  for (int rep = 0; rep < 3; ++rep) {
+    cudaEventRecord(e0);
+    launch();
+    cudaEventRecord(e1);
+    cudaError_t e = cudaEventSynchronize(e1);
+    if (e != cudaSuccess) return fail((int)e, cudaGetErrorString(e));
+    float ms = 0;
+    cudaEventElapsedTime(&ms, e0, e1);
+    best = std::min(best, (double)ms);
+  }
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  *ms_out = best;
+  CK(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int gpsat_microbench(int device, int which, int param, int nk, double* tflops_out) {
+  if (!tflops_out) return fail(GPSAT_EINVAL, "bad argument");
+  CK(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  CK(cudaGetDeviceProperties(&prop, device));
+  const int nsm = prop.multiProcessorCount;
+  double* buf = nullptr;
+  double ms = 0;
+  int r = 0;
+  if (which < 4) {
+    CK(cudaMalloc(&buf, 64));
+    const int grid = nsm * std::max(1, param), iters = nk;
+    const int nch = 1 << which;
+    if (which == 0) r = time_launch([&] { k_dmma_chain<1><<<grid, 256>>>(iters, buf); }, &ms);
+    if (which == 1) r = time_launch([&] { k_dmma_chain<2><<<grid, 256>>>(iters, buf); }, &ms);
+    if (which == 2) r = time_launch([&] { k_dmma_chain<4><<<grid, 256>>>(iters, buf); }, &ms);
+    if (which == 3) r = time_launch([&] { k_dmma_chain<8><<<grid, 256>>>(iters, buf); }, &ms);
+    *tflops_out = 2.0 * 256 * nch * (double)iters * 8 * grid / (ms * 1e-3) / 1e12;
+  } else if (which == 20 || which == 21) {
+    CK(cudaMalloc(&buf, 64));
+    const int grid = nsm * 4;
+    if (which == 20) {
+      r = time_launch([&] { k_pipe_mix<<<grid, 256>>>(nk, param, buf); }, &ms);
+      *tflops_out = ms;   // milliseconds: compare modes 1, 2, 3
+    } else {
+      r = time_launch([&] { k_kern_rate<<<grid, 256>>>(nk, param, buf); }, &ms);
+      *tflops_out = (double)grid * 256 * nk / (ms * 1e-3) / 1e9;   // G entries / s
+    }
+  } else {
+    const long tiles_per_cta = 64;
+    const size_t bytes = (size_t)(param == 1 ? nsm : 1) * tiles_per_cta * TILE_BYTES;
+    CK(cudaMalloc(&buf, bytes + 64));
+    CK(cudaMemset(buf, 0, bytes + 64));
+    if (which == 10) {
+      CK(cudaFuncSetAttribute(k_gemm1_bench, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * TILE_BYTES));
+      r = time_launch([&] { k_gemm1_bench<<<nsm, NTHREADS, 4 * TILE_BYTES>>>(buf, tiles_per_cta, nk, param, buf + bytes / 8); }, &ms);
+      *tflops_out = 2.0 * 64 * 64 * 64 * (double)nk * nsm / (ms * 1e-3) / 1e12;
+    } else {
+      auto kern = (which == 11) ? k_gemm2_bench<false, false> : (which == 12 ? k_gemm2_bench<true, true> : k_gemm2_bench<false, true>);
+      CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, G2_SMEM_ELEMS * 8));
+      r = time_launch([&] { kern<<<nsm, NTHREADS, G2_SMEM_ELEMS * 8>>>(buf, tiles_per_cta, nk, param, buf + bytes / 8); }, &ms);
+      *tflops_out = 2.0 * 128 * 128 * 64 * (double)nk * nsm / (ms * 1e-3) / 1e12;
+    }
+  }
+  cudaFree(buf);
+  return r;
 }
 
 // ---- host-side L-BFGS hooks (same code the device runs) ----

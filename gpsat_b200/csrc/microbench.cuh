@@ -1,0 +1,124 @@
+// gpsat_b200: micro-benchmarks that establish the roofline denominators and the efficiency of the
+// GEMM cores in isolation (used by bench.py / profiles, not by the product path).
+#pragma once
+#include "gemm_core.cuh"
+#include "gemm2.cuh"
+
+namespace gpsat {
+
+// register-resident DMMA chains: NCH independent accumulators per warp
+template <int NCH>
+__global__ void __launch_bounds__(256) k_dmma_chain(int iters, double* sink) {
+  double c[NCH][2];
+#pragma unroll
+  for (int k = 0; k < NCH; ++k) c[k][0] = c[k][1] = 0.0;
+  double a = 1.0 + threadIdx.x * 1e-9, b = 1.0 - threadIdx.x * 1e-9;
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int k = 0; k < NCH; ++k) dmma884(c[k][0], c[k][1], a, b);
+  }
+  double s = 0.0;
+#pragma unroll
+  for (int k = 0; k < NCH; ++k) s += c[k][0] + c[k][1];
+  if (s == 12345.678) sink[0] = s;
+}
+
+// do the FP64 FMA pipe and the DMMA pipe run concurrently?  warps 0-3 of each CTA issue DMMA chains
+// (mode & 1), warps 4-7 issue DFMA chains (mode & 2)
+__global__ void __launch_bounds__(256) k_pipe_mix(int iters, int mode, double* sink) {
+  const int warp = threadIdx.x >> 5;
+  double s = 0.0;
+  if (warp < 4) {
+    if (mode & 1) {
+      double c[8][2];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) c[k][0] = c[k][1] = 0.0;
+      double a = 1.0 + threadIdx.x * 1e-9, b = 1.0 - threadIdx.x * 1e-9;
+      for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) dmma884(c[k][0], c[k][1], a, b);
+      }
+#pragma unroll
+      for (int k = 0; k < 8; ++k) s += c[k][0] + c[k][1];
+    }
+  } else if (mode & 2) {
+    double c[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) c[k] = threadIdx.x * 1e-3 + k;
+    const double a = 1.0 + 1e-9 * threadIdx.x, b = 1e-12;
+    for (int it = 0; it < iters * 8; ++it) {     // 8 DFMA per lane ~ same pipe time as one DMMA if rates match
+#pragma unroll
+      for (int k = 0; k < 8; ++k) c[k] = fma(c[k], a, b);
+    }
+#pragma unroll
+    for (int k = 0; k < 8; ++k) s += c[k];
+  }
+  if (s == 12345.678) sink[0] = s;
+}
+
+// throughput of the kernel-function evaluation itself (entries / s)
+__global__ void __launch_bounds__(256) k_kern_rate(int iters, int kid, double* sink) {
+  double r2 = 1e-3 * threadIdx.x + 1e-6 * blockIdx.x, s = 0.0;
+  for (int it = 0; it < iters; ++it) {
+    double k, h;
+    kern_eval(kid, r2, 0.5, k, h);
+    s += k + h;
+    r2 += 1e-4;
+  }
+  if (s == 12345.678) sink[0] = s;
+}
+
+// 128x128 supertile core: mode 0 = shared-memory resident operands (no global traffic),
+// mode 1 = stream nk k-tiles per CTA from a private region (HBM), mode 2 = all CTAs read the same tiles (L2)
+template <bool TA, bool TBm>
+__global__ void __launch_bounds__(NTHREADS, 1) k_gemm2_bench(const double* tiles, long tiles_per_cta, int nk, int mode,
+                                                             double* out) {
+  extern __shared__ __align__(128) double smem[];
+  Frag2 f;
+  Acc2 acc;
+  acc.zero();
+  if (mode == 0) {
+    for (int i = threadIdx.x; i < G2_STAGE_ELEMS; i += NTHREADS) smem[i] = 1e-3 * (i & 255);
+    __syncthreads();
+    for (int k = 0; k < 2 * nk; ++k) mma_half<TA, TBm>(acc, smem + f.ta * HALF_ELEMS, smem + (2 + f.tb) * HALF_ELEMS, f);
+  } else {
+    const double* base = tiles + (mode == 1 ? (long)blockIdx.x * tiles_per_cta * TILE_ELEMS : 0L);
+    gemm2_pipeline<TA, TBm>(
+        acc, smem, 0, nk,
+        [&](int k, int t) { return base + ((long)(4 * k + t) % tiles_per_cta) * TILE_ELEMS; },
+        [&](int k, int t) { return base + ((long)(4 * k + 2 + t) % tiles_per_cta) * TILE_ELEMS; }, f);
+  }
+  double s = 0.0;
+#pragma unroll
+  for (int mi = 0; mi < 8; ++mi)
+#pragma unroll
+    for (int ni = 0; ni < 4; ++ni) s += acc.c[mi][ni][0] + acc.c[mi][ni][1];
+  if (s == 12345.678) out[0] = s;
+}
+
+// 64x64 core (gemm_core.cuh), same modes
+__global__ void __launch_bounds__(NTHREADS, 1) k_gemm1_bench(const double* tiles, long tiles_per_cta, int nk, int mode,
+                                                             double* out) {
+  extern __shared__ __align__(128) double smem[];
+  FragCoord fc;
+  Acc acc;
+  acc.zero();
+  if (mode == 0) {
+    for (int i = threadIdx.x; i < 2 * TILE_ELEMS; i += NTHREADS) smem[i] = 1e-3 * (i & 255);
+    __syncthreads();
+    for (int k = 0; k < nk; ++k) mma_tile<false, false>(acc, smem, smem + TILE_ELEMS, fc);
+  } else {
+    const double* base = tiles + (mode == 1 ? (long)blockIdx.x * tiles_per_cta * TILE_ELEMS : 0L);
+    gemm_pipeline<false, false>(
+        acc, smem, 0, nk, [&](int k) { return base + ((long)(2 * k) % tiles_per_cta) * TILE_ELEMS; },
+        [&](int k) { return base + ((long)(2 * k + 1) % tiles_per_cta) * TILE_ELEMS; }, fc);
+  }
+  double s = 0.0;
+#pragma unroll
+  for (int mi = 0; mi < 2; ++mi)
+#pragma unroll
+    for (int ni = 0; ni < 4; ++ni) s += acc.c[mi][ni][0] + acc.c[mi][ni][1];
+  if (s == 12345.678) out[0] = s;
+}
+
+}  // namespace gpsat

@@ -166,6 +166,12 @@ int gpsat_get_profile(gpsat_handle* h, double* ms_potrf, double* ms_trtri, doubl
  * this GPU measured with register-resident accumulator chains (no memory traffic). */
 int gpsat_dmma_peak(int device, int iters, double* tflops_out, double* ms_out);
 
+/* isolated core measurements (profiles/): which 0..3 = register DMMA chains with 1/2/4/8
+ * accumulators per warp and `param` CTAs of 8 warps per SM (nk = iterations); 10 = 64x64 core,
+ * 11/12/13 = 128x128 core (NT / TN / NN operand orientations) with param = 0 shared-memory resident,
+ * 1 streaming private tiles (HBM), 2 all CTAs on the same tiles (L2); nk = 64-deep k steps. */
+int gpsat_microbench(int device, int which, int param, int nk, double* tflops_out);
+
 /* host-side (CPU) entry to the SAME L-BFGS state machine the device runs, for CPU unit tests of
  * the optimiser logic against scipy (no GPU needed). */
 size_t gpsat_lbfgs_state_bytes(void);

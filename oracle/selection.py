@@ -15,6 +15,7 @@ from __future__ import annotations
 import operator
 
 import numpy as np
+import pandas as pd
 
 _COMP = {">=": operator.ge, ">": operator.gt, "==": operator.eq, "<": operator.lt, "<=": operator.le,
          "!=": operator.ne}
@@ -39,7 +40,7 @@ def expand_where_list(global_select, local_select, ref_loc: dict):
         assert all(c in gs for c in ("loc_col", "src_col", "func"))
         func = gs["func"]
         if isinstance(func, str):
-            func = eval(func)  # noqa: S307 - same contract as the reference's config lambdas
+            func = eval(func, {"np": np, "pd": pd})  # noqa: S307 - same contract as the reference's config lambdas
         for ls in local_select:
             if gs["loc_col"] == ls["col"]:
                 out.append({"col": gs["src_col"], "comp": ls["comp"],

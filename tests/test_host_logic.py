@@ -1,0 +1,108 @@
+"""CPU tests of the host-side mirror of the reference interface (no GPU, no oracle on the product path:
+the oracle appears here only as the checker)."""
+import numpy as np
+import pandas as pd
+import pytest
+
+from gpsat_b200.batched import ModelSpec, sel_terms
+from gpsat_b200.local_experts import _apply_where, _where_list, pretty_print_class
+from gpsat_b200.model import B200GPRModel, get_model
+from gpsat_b200.params import HyperParams
+from oracle import gpr
+
+
+def test_constraints_match_oracle_worked_example():
+    """SURVEY 8a row M4 worked example: inline config -> l in [2e-13, 12] x2, [1e-8, 9]; noise start 0.005625."""
+    X = np.random.default_rng(1).normal(size=(10, 3))
+    cons = {"lengthscales": {"low": [1e-8] * 3, "high": [600000, 600000, 9], "scale": True},
+            "likelihood_variance": {"low": 0.00125, "high": 0.01}}
+    o = gpr.OracleGPRModel(coords=X.copy(), obs=X[:, 0].copy(), coords_scale=[50_000, 50_000, 1])
+    o.set_parameter_constraints({k: dict(v) for k, v in cons.items()}, move_within_tol=True, tol=1e-2)
+    m = B200GPRModel(coords=X.copy(), obs=X[:, 0].copy(), coords_scale=[50_000, 50_000, 1], verbose=False)
+    m.set_parameter_constraints({k: dict(v) for k, v in cons.items()}, move_within_tol=True, tol=1e-2)
+    np.testing.assert_array_equal(m.get_lengthscales(), o.get_lengthscales())
+    assert m.get_likelihood_variance() == o.get_likelihood_variance() == pytest.approx(0.005625, abs=1e-15)
+    k1, l1, h1 = m._hp.transforms()
+    k2, l2, h2 = o._transforms_flat()
+    np.testing.assert_array_equal(k1, k2)
+    np.testing.assert_array_equal(l1, l2)
+    np.testing.assert_array_equal(h1, h2)
+    # the batched spec produces the same start point and bijectors from the model config
+    spec = ModelSpec.from_model_config({"init_params": {"coords_scale": [50_000, 50_000, 1]},
+                                        "constraints": {k: {kk: vv for kk, vv in v.items() if kk != "scale"}
+                                                        for k, v in cons.items()}})
+    hp = spec.hyper_params(3)
+    np.testing.assert_array_equal(hp.theta(), m._hp.theta())
+    np.testing.assert_array_equal(hp.transforms()[2], h1)
+
+
+def test_model_interface_without_gpu():
+    """postprocessing.smooth_hyperparameters builds a model on a 1-row frame just to read param_names."""
+    df = pd.DataFrame({"x": [0.0], "y": [1.0], "t": [2.0], "obs": [0.5]})
+    m = B200GPRModel(data=df, coords_col=["x", "y", "t"], obs_col="obs", expert_loc=np.zeros(3), verbose=False)
+    assert m.param_names == ["lengthscales", "kernel_variance", "likelihood_variance"]
+    p = m.get_parameters()
+    np.testing.assert_array_equal(p["lengthscales"], np.ones(3))
+    assert p["kernel_variance"] == 1.0 and p["likelihood_variance"] == 1.0
+    m.set_parameters(lengthscales=[2.0, 3.0, 4.0], kernel_variance=np.array([0.5]), likelihood_variance=1e-9)
+    assert m.get_likelihood_variance() == 1e-6      # clipped to gpflow's lower bound
+    assert m.get_parameters("kernel_variance", return_dict=False) == [0.5]
+    with pytest.raises(AssertionError):
+        m.get_parameters("nope")
+    with pytest.raises(AssertionError):
+        m.set_parameters(nope=1)
+    with pytest.raises(AssertionError):
+        B200GPRModel(coords=np.array([[np.nan]]), obs=np.array([1.0]))
+    assert get_model("B200GPRModel") is B200GPRModel
+    with pytest.raises(NotImplementedError):
+        get_model("sklearnGPRModel")
+    # obs_mean: only 'local' is honoured (base_model.py:195-200)
+    m2 = B200GPRModel(coords=np.arange(4.0), obs=np.array([1.0, 2, 3, 4]), obs_mean=7.0, verbose=False)
+    assert m2.obs_mean[0, 0] == 0 and m2.obs[:, 0].tolist() == [1, 2, 3, 4]
+    m3 = B200GPRModel(coords=np.arange(4.0), obs=np.array([1.0, 2, 3, 4]), obs_mean="local", obs_scale=2, verbose=False)
+    assert m3.obs_mean[0, 0] == 2.5 and m3.obs[:, 0].tolist() == [-0.75, -0.25, 0.25, 0.75]
+
+
+def test_numerical_methods_fail_loudly_without_cuda():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    m = B200GPRModel(coords=np.arange(4.0), obs=np.array([1.0, 2, 3, 4]), verbose=False)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        m.get_objective_function_value()
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        m.optimise_parameters()
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        m.predict(np.array([[1.0]]))
+
+
+def test_hyperparams_fixed_mask_and_roundtrip():
+    hp = HyperParams(3, [1, 2, 3], 0.5, 0.1)
+    np.testing.assert_array_equal(hp.trainable_mask(["likelihood_variance", "kernel_variance"]), [1, 1, 1, 0, 0])
+    np.testing.assert_array_equal(hp.trainable_mask(["lengthscales"]), [0, 0, 0, 1, 1])
+    th = hp.theta()
+    hp2 = HyperParams(3)
+    hp2.set_theta(th)
+    np.testing.assert_array_equal(hp2.theta(), th)
+    k, lo, hi = hp.transforms()
+    assert k.tolist() == [0] * 5 and lo[4] == 1e-6
+    with pytest.raises(AssertionError):
+        hp.set_constraints("lengthscales", [1, 1], [2, 2])
+
+
+def test_sel_terms_and_where_list():
+    ls = [{"col": "t", "comp": "<=", "val": 4}, {"col": "t", "comp": ">=", "val": -4},
+          {"col": ["x", "y"], "comp": "<", "val": 300_000}]
+    t = sel_terms(ls, ["x", "y", "t", "obs"], ["x", "y", "t"])
+    assert [q["type"] for q in t] == [0, 0, 1]
+    assert t[0]["cols"] == [2] and t[2]["cols"] == [0, 1] and t[2]["val"] == 300_000
+    gs = [{"col": "lat", "comp": ">=", "val": 60},
+          {"loc_col": "t", "src_col": "date", "func": "lambda x,y: np.datetime64(pd.to_datetime(x+y, unit='D'))"}]
+    w = _where_list(gs, ls, {"x": 0.0, "y": 0.0, "t": 18326.0})
+    assert w[0] == gs[0]
+    assert w[1] == {"col": "date", "comp": "<=", "val": np.datetime64("2020-03-09")}
+    assert w[2] == {"col": "date", "comp": ">=", "val": np.datetime64("2020-03-01")}
+    df = pd.DataFrame({"lat": [50.0, 70.0, 80.0],
+                       "date": pd.to_datetime(["2020-03-05", "2020-03-05", "2020-04-01"])})
+    assert _apply_where(df, w).index.tolist() == [1]
+    assert pretty_print_class(B200GPRModel) == "gpsat_b200.model.B200GPRModel"
