@@ -239,11 +239,12 @@ def run_b200(args):
     l0 = eng.launch_count()
     ev0, ev1 = torch.cuda.Event(True), torch.cuda.Event(True)
     ev0.record()
-    n_done, nfev_sum, nobs = 0, 0, []
+    n_done, nfev_sum, nobs, nfev_max = 0, 0, [], 0
     for s in range(args.steps):
         r = step_device(args.warmup + s)
         n_done += r["n_valid"]
         nfev_sum += int(r["nfev"].sum().item()) if "nfev" in r else 0
+        nfev_max = max(nfev_max, int(r["nfev"].max().item()) if "nfev" in r else 0)
         nobs.append(r["num_obs"].float().mean().item())
     ev1.record()
     barrier()
@@ -309,7 +310,7 @@ def run_b200(args):
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": f"{w['name']}: {w['describe']}", "experts_per_step_per_gpu": B,
-                       "mean_obs_per_expert": float(np.mean(nobs)), "mean_nfev": nfev_sum / max(n_done, 1),
+                       "mean_obs_per_expert": float(np.mean(nobs)), "mean_nfev": nfev_sum / max(n_done, 1), "max_nfev": nfev_max,
                        "l2": "inputs larger than L2 (factor workspaces are GBs per step)"},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": int(d2h)},
             "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu}

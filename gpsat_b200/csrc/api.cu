@@ -45,7 +45,7 @@ struct gpsat_handle {
   std::vector<cudaEvent_t> ev;
   size_t ev_used = 0;
   std::vector<double> ev_flops;  // N^3/3 summed over active slots for each recorded round
-  Buf Lt, Xt, coords, yobs, ints, theta, logdet, gpart, fout, gout, states, order, pslot, pres, scratch, items;
+  Buf Lt, Xt, Kt, quad, coords, yobs, ints, theta, logdet, gpart, fout, gout, states, order, pslot, pres, scratch, items;
   int* host_ints = nullptr;  // pinned
   size_t host_ints_cap = 0;
   bool attrs_set = false;
@@ -100,11 +100,12 @@ extern "C" int gpsat_create(gpsat_handle** out, int device, size_t mem_budget_by
   size_t free_b = 0, total_b = 0;
   CK(cudaMemGetInfo(&free_b, &total_b));
   h->budget = mem_budget_bytes ? mem_budget_bytes : (size_t)(0.7 * (double)free_b);
-  CK(cudaFuncSetAttribute(k_potrf_update, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-  CK(cudaFuncSetAttribute(k_potrf_trsm, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-  CK(cudaFuncSetAttribute(k_trtri_step, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-  CK(cudaFuncSetAttribute(k_lauum_trace, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-  CK(cudaFuncSetAttribute(k_predict, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+  CK(cudaFuncSetAttribute(k_potrf_update2, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM2_BYTES));
+  CK(cudaFuncSetAttribute(k_potrf_trsm2, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM2_BYTES));
+  CK(cudaFuncSetAttribute(k_trtri_pass1, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM2_BYTES));
+  CK(cudaFuncSetAttribute(k_trtri_pass2, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM2_BYTES));
+  CK(cudaFuncSetAttribute(k_lauum2, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM2_BYTES));
+  CK(cudaFuncSetAttribute(k_predict2, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM2_BYTES));
   *out = h;
   return 0;
 }
@@ -112,7 +113,7 @@ extern "C" int gpsat_create(gpsat_handle** out, int device, size_t mem_budget_by
 extern "C" int gpsat_destroy(gpsat_handle* h) {
   if (!h) return 0;
   cudaSetDevice(h->device);
-  Buf* bs[] = {&h->Lt, &h->Xt, &h->coords, &h->yobs, &h->ints, &h->theta, &h->logdet, &h->gpart,
+  Buf* bs[] = {&h->Lt, &h->Xt, &h->Kt, &h->quad, &h->coords, &h->yobs, &h->ints, &h->theta, &h->logdet, &h->gpart,
                &h->fout, &h->gout, &h->states, &h->order, &h->pslot, &h->pres, &h->scratch, &h->items};
   for (Buf* b : bs)
     if (b->p) cudaFree(b->p);
@@ -149,7 +150,7 @@ struct Plan {
 static size_t slot_bytes(int nbmax) {
   const size_t ntmax = (size_t)nbmax * (nbmax + 1) / 2;
   const size_t npmax = (size_t)nbmax * TB;
-  return 2 * ntmax * TILE_BYTES + (MAXD + 1) * npmax * 8 + nbmax * 8 + ntmax * NG * 8 + sizeof(LbfgsState) + 256;
+  return 3 * ntmax * TILE_BYTES + (MAXD + 1) * npmax * 8 + nbmax * 8 + ntmax * NG * 8 + sizeof(LbfgsState) + 256;
 }
 
 static int make_plan(gpsat_handle* h, const gpsat_batch* b, Plan& pl, size_t extra_per_slot = 0) {
@@ -183,6 +184,8 @@ static int setup_work(gpsat_handle* h, const gpsat_batch* b, const Plan& pl, Wor
   const int S = pl.S;
   ENS(h->Lt, (size_t)S * pl.ntmax * TILE_BYTES);
   ENS(h->Xt, (size_t)S * pl.ntmax * TILE_BYTES);
+  ENS(h->Kt, (size_t)S * pl.ntmax * TILE_BYTES);
+  ENS(h->quad, (size_t)S * 8);
   ENS(h->coords, (size_t)S * MAXD * pl.npmax * 8);
   ENS(h->yobs, (size_t)S * pl.npmax * 8);
   ENS(h->ints, (size_t)(6 * S + 8) * sizeof(int));
@@ -202,7 +205,7 @@ static int setup_work(gpsat_handle* h, const gpsat_batch* b, const Plan& pl, Wor
   SlotCtx& c = w.c;
   c.S = S; c.D = b->D; c.kid = b->kernel_id; c.nbmax = pl.nbmax; c.npmax = pl.npmax; c.ntmax = pl.ntmax;
   c.tile_stride = (long)pl.ntmax * TILE_ELEMS;
-  c.Lt = (double*)h->Lt.p; c.Xt = (double*)h->Xt.p;
+  c.Lt = (double*)h->Lt.p; c.Xt = (double*)h->Xt.p; c.Kt = (double*)h->Kt.p; c.quad = (double*)h->quad.p;
   c.coords = (double*)h->coords.p; c.yobs = (double*)h->yobs.p;
   c.n = ip; c.nb = ip + S; c.active = ip + 2 * S; c.fail = ip + 3 * S;
   c.theta = (double*)h->theta.p; c.logdet_part = (double*)h->logdet.p; c.gpart = (double*)h->gpart.p;
@@ -236,33 +239,41 @@ static cudaEvent_t next_event(gpsat_handle* h) {
   return h->ev[h->ev_used++];
 }
 
-// one objective evaluation for all active slots.  nbm: max blocks among active slots.
+// one objective evaluation for all active slots.  nbm: max 64-blocks among active slots.
 static int run_round(gpsat_handle* h, const SlotCtx& c, int nbm, bool inverse, bool grad, cudaStream_t st,
                      double flops_third) {
   const bool prof = h->profiling;
+  const int nsr = (nbm + 1) / 2, ntm = nbm * (nbm + 1) / 2;
   if (prof) { cudaEventRecord(next_event(h), st); h->ev_flops.push_back(flops_third); }
-  for (int j = 0; j < nbm; ++j) {
-    k_potrf_update<<<dim3(nbm - j, c.S), NTHREADS, SMEM_BYTES, st>>>(c, j);
+  k_build<<<dim3(ntm, c.S), 256, 0, st>>>(c);
+  ++h->launches;
+  for (int J = 0; J < nsr; ++J) {
+    k_potrf_update2<<<dim3(nsr - J, c.S), NTHREADS, SMEM2_BYTES, st>>>(c, J);
     ++h->launches;
-    if (j + 1 < nbm) {
-      k_potrf_trsm<<<dim3(nbm - j - 1, c.S), NTHREADS, SMEM_BYTES, st>>>(c, j);
+    if (J + 1 < nsr) {
+      k_potrf_trsm2<<<dim3(nsr - J - 1, c.S), NTHREADS, SMEM2_BYTES, st>>>(c, J);
       ++h->launches;
     }
   }
+  k_quad<<<c.S, NTHREADS, 0, st>>>(c);
+  ++h->launches;
   if (prof) cudaEventRecord(next_event(h), st);
   if (inverse) {
-    for (int sd = 1; sd < nbm; ++sd) {
-      k_trtri_step<<<dim3(nbm - sd, c.S), NTHREADS, SMEM_BYTES, st>>>(c, sd);
-      ++h->launches;
+    for (int hh = 1; hh < nsr; hh *= 2) {
+      const int nblk = (nsr + 2 * hh - 1) / (2 * hh);
+      k_trtri_pass1<<<dim3(nblk * hh * hh, c.S), NTHREADS, SMEM2_BYTES, st>>>(c, hh);
+      k_trtri_pass2<<<dim3(nblk * hh * hh, c.S), NTHREADS, SMEM2_BYTES, st>>>(c, hh);
+      h->launches += 2;
     }
   }
   if (prof) cudaEventRecord(next_event(h), st);
   if (grad) {
-    k_lauum_trace<<<dim3(nbm * (nbm + 1) / 2, c.S), NTHREADS, SMEM_BYTES, st>>>(c);
-    ++h->launches;
+    k_lauum2<<<dim3(nsr * (nsr + 1) / 2, c.S), NTHREADS, SMEM2_BYTES, st>>>(c);
+    k_grad_trace<<<dim3(ntm, c.S), 256, 0, st>>>(c);
+    h->launches += 2;
   }
   if (prof) cudaEventRecord(next_event(h), st);
-  k_finalize<<<c.S, NTHREADS, 0, st>>>(c, grad ? 1 : 0);
+  k_finalize2<<<c.S, NTHREADS, 0, st>>>(c, grad ? 1 : 0);
   ++h->launches;
   if (prof) cudaEventRecord(next_event(h), st);
   CK(cudaGetLastError());
@@ -426,17 +437,19 @@ extern "C" int gpsat_gpr_predict(gpsat_handle* h, const gpsat_batch* b, const do
   r = setup_work(h, b, pl, w, st);
   if (r) return r;
   const int S = pl.S;
-  const int grid = h->n_sm;
   ENS(h->pslot, (size_t)S * MAXD * ppmax * 8 + (size_t)(S + 8) * sizeof(int) + MAXD * 8);
   ENS(h->pres, (size_t)2 * S * ppmax * 8);
-  ENS(h->scratch, (size_t)grid * pl.nbmax * TILE_BYTES);
+  // scratch for the cross-covariance tiles of one wave of items (item = slot x pair of 64-blocks)
+  const size_t item_bytes = (size_t)pl.nbmax * 2 * TILE_BYTES;
+  size_t scratch_budget = std::min<size_t>((size_t)8 << 30, h->budget / 8);
+  int wave = (int)std::max<size_t>(1, scratch_budget / item_bytes);
   double* pslot = (double*)h->pslot.p;
   double* cs_dev = pslot + (size_t)S * MAXD * ppmax;
   int* np_dev = (int*)(cs_dev + MAXD);
   BatchIn bi = make_batch_in(b, theta_dev, (const int*)h->order.p);
   CK(cudaMemcpyAsync(cs_dev, bi.coords_scale, MAXD * 8, cudaMemcpyHostToDevice, st));
   TransformSpec tr = identity_transforms(b->D);
-  std::vector<int> items;
+  std::vector<int> islot, ipb;
   for (int first = 0; first < E; first += S) {
     const int count = std::min(S, E - first);
     k_slot_init<<<S, NTHREADS, 0, st>>>(w.c, w.a, bi, tr, first, count, 0);
@@ -447,16 +460,18 @@ extern "C" int gpsat_gpr_predict(gpsat_handle* h, const gpsat_batch* b, const do
     if (r) return r;
     k_pred_load<<<S, NTHREADS, 0, st>>>(w.a, count, b->D, pcoords_dev, poff_dev, cs_dev, pslot, np_dev, ppmax);
     ++h->launches;
-    items.clear();
-    std::vector<int> islot, ipb;
+    islot.clear();
+    ipb.clear();
     for (int s = 0; s < count; ++s) {
       const int e = pl.order[first + s];
       const int npb = (int)((poff_host[e + 1] - poff_host[e] + TB - 1) / TB);
-      for (int pb = 0; pb < npb; ++pb) { islot.push_back(s); ipb.push_back(pb); }
+      for (int pb = 0; pb < npb; pb += 2) { islot.push_back(s); ipb.push_back(pb); }
     }
     const int n_items = (int)islot.size();
     if (n_items > 0) {
+      wave = std::min(wave, n_items);
       ENS(h->items, (size_t)2 * n_items * sizeof(int));
+      ENS(h->scratch, (size_t)wave * item_bytes);
       int* it_dev = (int*)h->items.p;
       // pageable copies are staged synchronously by the runtime; vectors can be reused afterwards
       CK(cudaMemcpyAsync(it_dev, islot.data(), (size_t)n_items * sizeof(int), cudaMemcpyHostToDevice, st));
@@ -464,12 +479,18 @@ extern "C" int gpsat_gpr_predict(gpsat_handle* h, const gpsat_batch* b, const do
       CK(cudaStreamSynchronize(st));
       PredCtx p;
       p.ppmax = ppmax; p.pcoords = pslot; p.np = np_dev;
-      p.item_slot = it_dev; p.item_pb = it_dev + n_items; p.n_items = n_items;
+      p.item_slot = it_dev; p.item_pb = it_dev + n_items;
       p.scratch = (double*)h->scratch.p;
       p.fmean = (double*)h->pres.p;
       p.fvar = (double*)h->pres.p + (size_t)S * ppmax;
-      k_predict<<<std::min(grid, n_items), NTHREADS, SMEM_BYTES, st>>>(w.c, p);
-      ++h->launches;
+      const int nbm = nb_of(b->offsets_host, pl.order[first]);
+      for (int i0 = 0; i0 < n_items; i0 += wave) {
+        p.item0 = i0;
+        p.n_items = std::min(wave, n_items - i0);
+        k_build_xp<<<dim3(nbm, p.n_items), 256, 0, st>>>(w.c, p);
+        k_predict2<<<p.n_items, NTHREADS, SMEM2_BYTES, st>>>(w.c, p);
+        h->launches += 2;
+      }
       k_pred_scatter<<<S, NTHREADS, 0, st>>>(w.c, w.a, count, poff_dev, p.fmean, p.fvar, ppmax, fmean_dev,
                                              fvar_dev, yvar_dev, fobj_dev);
       ++h->launches;
@@ -510,10 +531,17 @@ extern "C" int gpsat_debug_factor(gpsat_handle* h, const gpsat_batch* b, const d
   BatchIn bi = make_batch_in(&b1, theta_dev, nullptr);
   TransformSpec tr = identity_transforms(b->D);
   k_slot_init<<<pl.S, NTHREADS, 0, st>>>(w.c, w.a, bi, tr, 0, 1, 0);
-  r = run_round(h, w.c, pl.nbmax, true, false, st, 0.0);
-  if (r) return r;
-  if (l_dense) k_unpack_tiles<<<dim3(pl.nbmax, pl.nbmax), 256, 0, st>>>(w.c.Lt, pl.nbmax, l_dense);
-  if (x_dense) k_unpack_tiles<<<dim3(pl.nbmax, pl.nbmax), 256, 0, st>>>(w.c.Xt, pl.nbmax, x_dense);
+  // L is recycled by the inverse: dump it after a factorisation-only round, then run the full round
+  if (l_dense) {
+    r = run_round(h, w.c, pl.nbmax, false, false, st, 0.0);
+    if (r) return r;
+    k_unpack_tiles<<<dim3(pl.nbmax, pl.nbmax), 256, 0, st>>>(w.c, 0, 0, pl.nbmax, l_dense);
+  }
+  if (x_dense) {
+    r = run_round(h, w.c, pl.nbmax, true, false, st, 0.0);
+    if (r) return r;
+    k_unpack_tiles<<<dim3(pl.nbmax, pl.nbmax), 256, 0, st>>>(w.c, 0, 1, pl.nbmax, x_dense);
+  }
   CK(cudaStreamSynchronize(st));
   harvest_profile(h, true, false);
   CK(cudaGetLastError());

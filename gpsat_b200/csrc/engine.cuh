@@ -5,7 +5,7 @@
 // refilled on the device from a work queue (atomic counter), so the batch stays full while
 // iteration counts differ between experts.
 #pragma once
-#include "gpr_kernels.cuh"
+#include "gpr2.cuh"
 #include "lbfgs.cuh"
 
 namespace gpsat {

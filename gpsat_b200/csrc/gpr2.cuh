@@ -1,0 +1,725 @@
+// gpsat_b200: batched exact-GPR kernels, generation 2 (128x128 supertile DMMA core).
+//
+// One objective evaluation for every active slot is
+//   k_build         K_aug tiles (kernel matrix + noise, augmented with the observation row) -> Kt
+//                   FP64 elementwise, high occupancy (the DMMA and DFMA pipes are the same hardware
+//                   on sm_100, so elementwise work cannot hide behind tensor work -- only its latency
+//                   can be hidden, by running it in its own many-warps kernel)
+//   k_potrf_*2      left-looking blocked Cholesky with 128-wide panels; the diagonal CTA factorises
+//                   its 128x128 block in shared memory and also emits the block's inverse
+//   k_quad          a'a from the augmented row of the factor (row N of L_aug is a' = (L^-1 y)')
+//   k_trtri_*       X = L_aug^-1 by recursive doubling: at level l every 2^l-supertile block gets its
+//                   lower-left square X21 = -X22 (L21 X11) from two batched GEMM passes.  L21 is dead
+//                   after pass 1, so X21 is written over it: the inverse ends up with its 128x128
+//                   diagonal blocks in Xt and everything else in Lt (see x_tile()).
+//   k_lauum2        tiles of X'X = K_y^-1 + alpha alpha' -> Kt (K is dead after the factorisation)
+//   k_grad_trace    G_k = sum_ij (K^-1 - alpha alpha')_ij dK_ij/dtheta_k, FP64 elementwise, high occupancy
+//   k_finalize2     -LML and d(-LML)/dtheta
+// Prediction (row F1): k_build_xp writes cross-covariance tiles, k_predict2 accumulates
+// A = X K_xp supertile by supertile with a fused column sum of squares; the augmented row of X
+// (-alpha') yields the posterior mean.
+#pragma once
+#include "gemm_core.cuh"
+#include "gemm2.cuh"
+
+namespace gpsat {
+
+constexpr int NG = MAXP;                              // gradient partials per tile
+// diagonal-block workspace of k_potrf_update2: a[64][65] + inv[64][68] + 4 tiles
+constexpr int LDA = 65;
+constexpr int LDI = 68;
+constexpr int DIAG_ELEMS = TB * LDA + TB * LDI + 4 * TILE_ELEMS;            // 24896
+constexpr int G2_AUX = 2 * MAXD * TB + 2 * TB + 64;
+constexpr int SMEM2_ELEMS = (DIAG_ELEMS > G2_SMEM_ELEMS ? DIAG_ELEMS : G2_SMEM_ELEMS) + G2_AUX;
+constexpr int SMEM2_BYTES = SMEM2_ELEMS * 8;
+
+struct SlotCtx {
+  int S, D, kid, nbmax, npmax, ntmax;
+  long tile_stride;         // doubles per slot in Lt / Xt / Kt (= ntmax * TILE_ELEMS)
+  double* Lt;               // [S][ntmax][4096] packed lower tiles: L_aug, later the off-diagonal part of X
+  double* Xt;               // [S][ntmax][4096] diagonal 128-blocks of X = L_aug^-1 (+ scratch T)
+  double* Kt;               // [S][ntmax][4096] K_aug tiles, later X'X tiles
+  double* coords;           // [S][MAXD][npmax]  coordinates / coords_scale
+  double* yobs;             // [S][npmax]        (obs - mean) / scale
+  int* n;                   // [S] observations per slot
+  int* nb;                  // [S] 64-blocks of the augmented matrix = n/64 + 1
+  int* active;              // [S]
+  double* theta;            // [S][MAXP] lengthscales[D], kernel variance, likelihood variance
+  double* logdet_part;      // [S][nbmax]
+  double* quad;             // [S] a'a
+  double* gpart;            // [S][ntmax][NG]
+  int* fail;                // [S] set when a pivot is not positive
+  double* fout;             // [S]  -LML
+  double* gout;             // [S][MAXP] d(-LML)/dtheta (constrained parameters)
+};
+
+__device__ __forceinline__ double* tile_ptr(double* base, int i, int j) {
+  return base + tri_index(i, j) * TILE_ELEMS;
+}
+// where tile (i, j), i >= j, of X = L_aug^-1 lives after k_trtri_* (see header comment)
+__device__ __forceinline__ double* x_tile(const SlotCtx& c, int s, int i, int j) {
+  double* base = ((i >> 1) == (j >> 1)) ? c.Xt : c.Lt;
+  return base + (long)s * c.tile_stride + tri_index(i, j) * TILE_ELEMS;
+}
+__device__ __forceinline__ void tri_decode(int t, int& i, int& j) {
+  i = (int)((sqrt(8.0 * t + 1.0) - 1.0) * 0.5);
+  while ((long)(i + 1) * (i + 2) / 2 <= t) ++i;
+  while ((long)i * (i + 1) / 2 > t) --i;
+  j = t - (int)((long)i * (i + 1) / 2);
+}
+
+// stage the (scaled-by-1/l) coordinates of block `blk` into dst[MAXD][64]
+__device__ __forceinline__ void stage_coords(double* dst, const double* coords_slot, int npmax, int D,
+                                             const double* th, int blk, int N) {
+  for (int t = threadIdx.x; t < D * TB; t += blockDim.x) {
+    const int d = t / TB, m = t % TB, g = blk * TB + m;
+    dst[d * TB + m] = (g < N) ? coords_slot[(long)d * npmax + g] / th[d] : 0.0;
+  }
+}
+
+// ------------------------------------------------------------------------------------
+// K1: kernel-matrix build.  grid (ntmax, S), 256 threads: thread = (row, 16-column group).
+// ------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256, 4) k_build(SlotCtx c) {
+  __shared__ double xi[MAXD * TB], xj[MAXD * TB], yj[TB];
+  const int s = blockIdx.y;
+  if (!c.active[s]) return;
+  const int nb = c.nb[s];
+  int i, j;
+  tri_decode(blockIdx.x, i, j);
+  if (i >= nb) return;
+  const int N = c.n[s];
+  const double* th = c.theta + s * MAXP;
+  const double* cs = c.coords + (long)s * MAXD * c.npmax;
+  stage_coords(xi, cs, c.npmax, c.D, th, i, N);
+  stage_coords(xj, cs, c.npmax, c.D, th, j, N);
+  if (threadIdx.x < TB) {
+    const int g = j * TB + threadIdx.x;
+    yj[threadIdx.x] = (g < N) ? c.yobs[(long)s * c.npmax + g] : 0.0;
+  }
+  __syncthreads();
+  const double kvar = th[c.D], nvar = th[c.D + 1];
+  const int m = threadIdx.x >> 2, c0 = (threadIdx.x & 3) * 16, gi = i * TB + m;
+  double* out = c.Kt + (long)s * c.tile_stride + tri_index(i, j) * TILE_ELEMS;
+  double xm[MAXD];
+#pragma unroll
+  for (int d = 0; d < MAXD; ++d) xm[d] = (d < c.D) ? xi[d * TB + m] : 0.0;
+#pragma unroll
+  for (int cc = 0; cc < 16; cc += 2) {
+    double v[2];
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {
+      const int n = c0 + cc + e, gj = j * TB + n;
+      double val;
+      if (gi < N && gj < N) {
+        double r2 = 0.0;
+#pragma unroll
+        for (int d = 0; d < MAXD; ++d)
+          if (d < c.D) {
+            const double df = xm[d] - xj[d * TB + n];
+            r2 += df * df;
+          }
+        val = kern_value(c.kid, r2, kvar);
+        if (gi == gj) val += nvar;
+      } else if (gi == N && gj < N) {
+        val = yj[n];
+      } else {
+        val = (gi == gj) ? 1.0 : 0.0;
+      }
+      v[e] = val;
+    }
+    *reinterpret_cast<double2*>(out + swz(m, c0 + cc)) = make_double2(v[0], v[1]);
+  }
+}
+
+// ------------------------------------------------------------------------------------
+// 64x64 diagonal block: Cholesky + triangular inverse in shared memory
+// a: [64][65] (lower part valid), inv: [64][68], dg: [64].  All NTHREADS threads call.
+// Global indices >= N (augmented row and padding) get a forced unit pivot.
+// ------------------------------------------------------------------------------------
+__device__ __forceinline__ void potf2_trtri_64(double* a, double* inv, double* dg, int g0, int N, int* fail_flag) {
+  const int tid = threadIdx.x;
+  const int rr = tid & 63, cg = tid >> 6;
+  for (int c = 0; c < TB; ++c) {
+    __syncthreads();
+    double d = a[c * LDA + c];
+    if (g0 + c >= N) d = 1.0;
+    if (!(d > 0.0)) {
+      if (tid == 0) *fail_flag = 1;
+      d = 1.0;
+    }
+    const double piv = sqrt(d);
+    if (tid < TB) {
+      if (tid > c) a[tid * LDA + c] *= (1.0 / piv);
+      else if (tid == c) dg[c] = piv;
+    }
+    __syncthreads();
+    const double lrc = a[rr * LDA + c];
+    for (int cc = c + 1 + cg; cc <= rr; cc += 4) a[rr * LDA + cc] -= lrc * a[cc * LDA + c];
+  }
+  __syncthreads();
+  const int col = tid >> 2, part = tid & 3;
+  for (int r = 0; r < TB; ++r) {
+    double sum = 0.0;
+    for (int k = part; k < r; k += 4) sum += a[r * LDA + k] * inv[k * LDI + col];
+    sum += __shfl_xor_sync(0xffffffffu, sum, 1);
+    sum += __shfl_xor_sync(0xffffffffu, sum, 2);
+    if (part == 0) inv[r * LDI + col] = (r >= col) ? (((r == col) ? 1.0 : 0.0) - sum) / dg[r] : 0.0;
+    __syncwarp();
+  }
+  __syncthreads();
+}
+
+// write L (from a/dg) and X (from inv) of a factorised diagonal block: L -> gL, X -> gX and sX (all swizzled)
+__device__ __forceinline__ void emit_diag(const double* a, const double* inv, const double* dg, double* gL,
+                                          double* gX, double* sX) {
+  for (int t = threadIdx.x; t < TILE_ELEMS; t += NTHREADS) {
+    const int r = t >> 6, cc = t & 63;
+    const double lv = (cc < r) ? a[r * LDA + cc] : ((cc == r) ? dg[r] : 0.0);
+    const double xv = inv[r * LDI + cc];
+    gL[swz(r, cc)] = lv;
+    gX[swz(r, cc)] = xv;
+    sX[swz(r, cc)] = xv;
+  }
+}
+__device__ __forceinline__ void emit_logdet(const double* dg, int g0, int N, double* out) {
+  if (threadIdx.x < 32) {
+    double ld = 0.0;
+    for (int k = threadIdx.x; k < TB; k += 32)
+      if (g0 + k < N) ld += log(dg[k]);
+    ld = warp_sum(ld);
+    if (threadIdx.x == 0) *out = ld;
+  }
+}
+
+// ------------------------------------------------------------------------------------
+// potrf panel J (tiles j0 = 2J, j1 = 2J+1), part 1:
+//   C_{i,j} = K_aug(i,j) - sum_{k<j0} L_ik L_jk'  for the 2x2 tile group of supertile row I >= J.
+// The diagonal CTA (I == J) factorises the 128x128 block: L00, L10, L11 -> Lt, X00, X10, X11 -> Xt.
+// grid (nsr_max - J, S)
+// ------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(NTHREADS, 1) k_potrf_update2(SlotCtx c, int J) {
+  extern __shared__ __align__(128) double smem[];
+  const int s = blockIdx.y;
+  if (!c.active[s]) return;
+  const int nb = c.nb[s];
+  const int I = J + blockIdx.x;
+  const int j0 = 2 * J, j1 = 2 * J + 1;
+  if (2 * I >= nb) return;
+  const int N = c.n[s];
+  double* Lt = c.Lt + (long)s * c.tile_stride;
+  double* Kt = c.Kt + (long)s * c.tile_stride;
+  Frag2 f;
+  Acc2 acc;
+  acc.zero();
+  gemm2_pipeline<false, false>(
+      acc, smem, 0, j0,
+      [&](int k, int t) -> const double* { return (2 * I + t < nb) ? tile_ptr(Lt, 2 * I + t, k) : nullptr; },
+      [&](int k, int t) -> const double* { return (j0 + t < nb) ? tile_ptr(Lt, j0 + t, k) : nullptr; }, f);
+  const int ti = 2 * I + f.ta, tj = j0 + f.tb;
+  const bool valid = (ti < nb) && (tj < nb) && (tj <= ti);
+  if (valid) {
+    const double* kt = tile_ptr(Kt, ti, tj);
+#pragma unroll
+    for (int mi = 0; mi < 8; ++mi)
+#pragma unroll
+      for (int ni = 0; ni < 4; ++ni) {
+        const double2 kv = *reinterpret_cast<const double2*>(kt + swz(f.row(mi), f.col(ni)));
+        acc.c[mi][ni][0] = kv.x - acc.c[mi][ni][0];
+        acc.c[mi][ni][1] = kv.y - acc.c[mi][ni][1];
+      }
+  }
+  if (I != J) {
+    if (valid) store_acc2(tile_ptr(Lt, ti, tj), acc, f);
+    return;
+  }
+  // ---- diagonal 128x128 block ----
+  double* Xt = c.Xt + (long)s * c.tile_stride;
+  double* a = smem;
+  double* inv = a + TB * LDA;
+  double* P0 = inv + TB * LDI;      // X00
+  double* P1 = P0 + TILE_ELEMS;     // C10, later M = L10 X00
+  double* P2 = P1 + TILE_ELEMS;     // C11, later X11
+  double* P3 = P2 + TILE_ELEMS;     // L10
+  double* dg = smem + (SMEM2_ELEMS - G2_AUX);
+  const bool two = (j1 < nb);
+  // the pipeline ended with a barrier: shared memory is free
+  if (f.ta == 0 && f.tb == 0) {
+#pragma unroll
+    for (int mi = 0; mi < 8; ++mi)
+#pragma unroll
+      for (int ni = 0; ni < 4; ++ni) {
+        a[f.row(mi) * LDA + f.col(ni)] = acc.c[mi][ni][0];
+        a[f.row(mi) * LDA + f.col(ni) + 1] = acc.c[mi][ni][1];
+      }
+  } else if (two && f.ta == 1 && f.tb == 0) {
+    store_acc2(P1, acc, f);
+  } else if (two && f.ta == 1 && f.tb == 1) {
+    store_acc2(P2, acc, f);
+  }
+  potf2_trtri_64(a, inv, dg, j0 * TB, N, c.fail + s);
+  emit_diag(a, inv, dg, tile_ptr(Lt, j0, j0), tile_ptr(Xt, j0, j0), P0);
+  emit_logdet(dg, j0 * TB, N, c.logdet_part + s * c.nbmax + j0);
+  __syncthreads();
+  if (!two) return;
+  FragCoord fc;
+  {  // L10 = C10 X00'
+    Acc t;
+    t.zero();
+    mma_tile<false, false>(t, P1, P0, fc);
+    store_acc_swizzled(P3, t, fc);
+    store_acc_swizzled(tile_ptr(Lt, j1, j0), t, fc);
+  }
+  __syncthreads();
+  {  // C11' = C11 - L10 L10'
+    Acc t;
+    t.zero();
+    mma_tile<false, false>(t, P3, P3, fc);
+#pragma unroll
+    for (int mi = 0; mi < 2; ++mi)
+#pragma unroll
+      for (int ni = 0; ni < 4; ++ni)
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          const int m = fc.row(mi), n = fc.col(ni) + e;
+          a[m * LDA + n] = P2[swz(m, n)] - t.c[mi][ni][e];
+        }
+  }
+  potf2_trtri_64(a, inv, dg, j1 * TB, N, c.fail + s);
+  emit_diag(a, inv, dg, tile_ptr(Lt, j1, j1), tile_ptr(Xt, j1, j1), P2);
+  emit_logdet(dg, j1 * TB, N, c.logdet_part + s * c.nbmax + j1);
+  __syncthreads();
+  {  // M = L10 X00
+    Acc t;
+    t.zero();
+    mma_tile<false, true>(t, P3, P0, fc);
+    store_acc_swizzled(P1, t, fc);
+  }
+  __syncthreads();
+  {  // X10 = -X11 M
+    Acc t;
+    t.zero();
+    mma_tile<false, true>(t, P2, P1, fc);
+    store_acc_swizzled(tile_ptr(Xt, j1, j0), t, fc, -1.0);
+  }
+}
+
+// potrf panel J, part 2: L_{I,panel} = C_{I,panel} * Ldiag^-T  for I > J.   grid (nsr_max - J - 1, S)
+__global__ void __launch_bounds__(NTHREADS, 1) k_potrf_trsm2(SlotCtx c, int J) {
+  extern __shared__ __align__(128) double smem[];
+  const int s = blockIdx.y;
+  if (!c.active[s]) return;
+  const int nb = c.nb[s];
+  const int I = J + 1 + blockIdx.x;
+  const int j0 = 2 * J;
+  if (2 * I >= nb) return;
+  double* Lt = c.Lt + (long)s * c.tile_stride;
+  double* Xt = c.Xt + (long)s * c.tile_stride;
+  Frag2 f;
+  Acc2 acc;
+  acc.zero();
+  const int kend = (j0 + 1 < nb) ? 2 : 1;
+  gemm2_pipeline<false, false>(
+      acc, smem, 0, kend,
+      [&](int k, int t) -> const double* { return (2 * I + t < nb) ? tile_ptr(Lt, 2 * I + t, j0 + k) : nullptr; },
+      [&](int k, int t) -> const double* {
+        return (t >= k && j0 + t < nb) ? tile_ptr(Xt, j0 + t, j0 + k) : nullptr;
+      },
+      f);
+  const int ti = 2 * I + f.ta, tj = j0 + f.tb;
+  if (ti < nb && tj < nb) store_acc2(tile_ptr(Lt, ti, tj), acc, f);
+}
+
+// a'a from the augmented row of the factor (must run before k_trtri_* recycles Lt).  grid (S)
+__global__ void __launch_bounds__(NTHREADS) k_quad(SlotCtx c) {
+  __shared__ double red[NTHREADS / 32];
+  const int s = blockIdx.x;
+  if (!c.active[s]) return;
+  const int N = c.n[s], nb = c.nb[s];
+  const int bN = nb - 1, rN = N - bN * TB;
+  const double* Lt = c.Lt + (long)s * c.tile_stride;
+  double v[1] = {0.0};
+  for (int idx = threadIdx.x; idx < N; idx += NTHREADS) {
+    const double a = Lt[tri_index(bN, idx >> 6) * TILE_ELEMS + swz(rN, idx & 63)];
+    v[0] += a * a;
+  }
+  block_sum<1>(v, red);
+  if (threadIdx.x == 0) c.quad[s] = v[0];
+}
+
+// ------------------------------------------------------------------------------------
+// trtri level (block = B supertiles, half h = B/2): lower-left square of every block.
+//   pass 1:  T   = L21 X11   -> Xt (scratch)          pass 2:  X21 = -X22 T  -> Lt (over the dead L21)
+// grid (nblk * h * h, S)
+// ------------------------------------------------------------------------------------
+__device__ __forceinline__ bool trtri_decode(int bx, int h, int nsr, int& P, int& Q, int& mid) {
+  const int hh = h * h;
+  const int m = bx / hh, rem = bx - m * hh;
+  const int s0 = m * 2 * h;
+  mid = s0 + h;
+  P = mid + rem / h;
+  Q = s0 + rem % h;
+  return P < nsr;
+}
+
+__global__ void __launch_bounds__(NTHREADS, 1) k_trtri_pass1(SlotCtx c, int h) {
+  extern __shared__ __align__(128) double smem[];
+  const int s = blockIdx.y;
+  if (!c.active[s]) return;
+  const int nb = c.nb[s], nsr = (nb + 1) >> 1;
+  int P, Q, mid;
+  if (!trtri_decode(blockIdx.x, h, nsr, P, Q, mid)) return;
+  double* Lt = c.Lt + (long)s * c.tile_stride;
+  double* Xt = c.Xt + (long)s * c.tile_stride;
+  Frag2 f;
+  Acc2 acc;
+  acc.zero();
+  gemm2_pipeline<false, true>(
+      acc, smem, 2 * Q, 2 * mid,
+      [&](int k, int t) -> const double* { return (2 * P + t < nb) ? tile_ptr(Lt, 2 * P + t, k) : nullptr; },
+      [&](int k, int t) -> const double* { return (k >= 2 * Q + t) ? x_tile(c, s, k, 2 * Q + t) : nullptr; }, f);
+  const int ti = 2 * P + f.ta, tj = 2 * Q + f.tb;
+  if (ti < nb) store_acc2(tile_ptr(Xt, ti, tj), acc, f);
+}
+
+__global__ void __launch_bounds__(NTHREADS, 1) k_trtri_pass2(SlotCtx c, int h) {
+  extern __shared__ __align__(128) double smem[];
+  const int s = blockIdx.y;
+  if (!c.active[s]) return;
+  const int nb = c.nb[s], nsr = (nb + 1) >> 1;
+  int P, Q, mid;
+  if (!trtri_decode(blockIdx.x, h, nsr, P, Q, mid)) return;
+  double* Lt = c.Lt + (long)s * c.tile_stride;
+  double* Xt = c.Xt + (long)s * c.tile_stride;
+  Frag2 f;
+  Acc2 acc;
+  acc.zero();
+  const int kend = (2 * P + 2 < nb) ? 2 * P + 2 : nb;
+  gemm2_pipeline<false, true>(
+      acc, smem, 2 * mid, kend,
+      [&](int k, int t) -> const double* {
+        return (2 * P + t < nb && k <= 2 * P + t) ? x_tile(c, s, 2 * P + t, k) : nullptr;
+      },
+      [&](int k, int t) -> const double* { return tile_ptr(Xt, k, 2 * Q + t); }, f);
+  const int ti = 2 * P + f.ta, tj = 2 * Q + f.tb;
+  if (ti < nb) store_acc2(tile_ptr(Lt, ti, tj), acc, f, -1.0);
+}
+
+// lauum: supertile (I, J), I >= J, of X'X -> Kt.   grid (nsr_max (nsr_max + 1) / 2, S)
+__global__ void __launch_bounds__(NTHREADS, 1) k_lauum2(SlotCtx c) {
+  extern __shared__ __align__(128) double smem[];
+  const int s = blockIdx.y;
+  if (!c.active[s]) return;
+  const int nb = c.nb[s], nsr = (nb + 1) >> 1;
+  int I, J;
+  tri_decode(blockIdx.x, I, J);
+  if (I >= nsr) return;
+  double* Kt = c.Kt + (long)s * c.tile_stride;
+  Frag2 f;
+  Acc2 acc;
+  acc.zero();
+  gemm2_pipeline<true, true>(
+      acc, smem, 2 * I, nb,
+      [&](int k, int t) -> const double* {
+        return (2 * I + t < nb && k >= 2 * I + t) ? x_tile(c, s, k, 2 * I + t) : nullptr;
+      },
+      [&](int k, int t) -> const double* {
+        return (2 * J + t < nb && k >= 2 * J + t) ? x_tile(c, s, k, 2 * J + t) : nullptr;
+      },
+      f);
+  const int ti = 2 * I + f.ta, tj = 2 * J + f.tb;
+  if (ti < nb && tj < nb && tj <= ti) store_acc2(tile_ptr(Kt, ti, tj), acc, f);
+}
+
+// gradient contraction per lower tile: reads (X'X)_ij from Kt, alpha from the augmented row of X.
+// grid (ntmax, S), 256 threads: thread = (row, 16-column group)
+__global__ void __launch_bounds__(256, 3) k_grad_trace(SlotCtx c) {
+  __shared__ double xi[MAXD * TB], xj[MAXD * TB], ai[TB], aj[TB], red[NG * 8];
+  const int s = blockIdx.y;
+  if (!c.active[s]) return;
+  const int nb = c.nb[s];
+  int i, j;
+  tri_decode(blockIdx.x, i, j);
+  if (i >= nb) return;
+  const int N = c.n[s];
+  const double* th = c.theta + s * MAXP;
+  const double* cs = c.coords + (long)s * MAXD * c.npmax;
+  stage_coords(xi, cs, c.npmax, c.D, th, i, N);
+  stage_coords(xj, cs, c.npmax, c.D, th, j, N);
+  const int bN = nb - 1, rN = N - bN * TB;
+  if (threadIdx.x < TB) {
+    ai[threadIdx.x] = -x_tile(c, s, bN, i)[swz(rN, threadIdx.x)];
+  } else if (threadIdx.x < 2 * TB) {
+    const int m = threadIdx.x - TB;
+    aj[m] = -x_tile(c, s, bN, j)[swz(rN, m)];
+  }
+  __syncthreads();
+  const double kvar = th[c.D];
+  const int m = threadIdx.x >> 2, c0 = (threadIdx.x & 3) * 16, gi = i * TB + m;
+  const double* w = c.Kt + (long)s * c.tile_stride + tri_index(i, j) * TILE_ELEMS;
+  double g[NG];
+#pragma unroll
+  for (int k = 0; k < NG; ++k) g[k] = 0.0;
+  if (gi < N) {
+    double xm[MAXD];
+#pragma unroll
+    for (int d = 0; d < MAXD; ++d) xm[d] = (d < c.D) ? xi[d * TB + m] : 0.0;
+    const double am2 = 2.0 * ai[m];
+#pragma unroll
+    for (int cc = 0; cc < 16; cc += 2) {
+      const double2 wv = *reinterpret_cast<const double2*>(w + swz(m, c0 + cc));
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const int n = c0 + cc + e, gj = j * TB + n;
+        if (gj < N) {
+          const double W = (e ? wv.y : wv.x) - am2 * aj[n];
+          double r2 = 0.0, d2[MAXD];
+#pragma unroll
+          for (int d = 0; d < MAXD; ++d) {
+            d2[d] = 0.0;
+            if (d < c.D) {
+              const double df = xm[d] - xj[d * TB + n];
+              d2[d] = df * df;
+              r2 += d2[d];
+            }
+          }
+          double kv, hv;
+          kern_eval(c.kid, r2, kvar, kv, hv);
+          const double wh = W * hv;
+#pragma unroll
+          for (int d = 0; d < MAXD; ++d) g[d] += wh * d2[d];
+          g[MAXD] += W * kv;
+          if (gi == gj) g[MAXD + 1] += W;
+        }
+      }
+    }
+  }
+  const double wgt = (i != j) ? 2.0 : 1.0;
+  block_sum<NG>(g, red);
+  if (threadIdx.x == 0) {
+    double* gp = c.gpart + ((long)s * c.ntmax + blockIdx.x) * NG;
+#pragma unroll
+    for (int k = 0; k < NG; ++k) gp[k] = wgt * g[k];
+  }
+}
+
+// finalize: -LML and d(-LML)/dtheta per slot.  grid (S), NTHREADS threads
+__global__ void __launch_bounds__(NTHREADS) k_finalize2(SlotCtx c, int with_grad) {
+  __shared__ double red[(NG + 1) * (NTHREADS / 32)];
+  const int s = blockIdx.x;
+  if (!c.active[s]) return;
+  const int N = c.n[s], nb = c.nb[s];
+  double v[NG + 1];
+#pragma unroll
+  for (int k = 0; k < NG + 1; ++k) v[k] = 0.0;
+  for (int k = threadIdx.x; k < nb; k += NTHREADS) v[NG] += c.logdet_part[s * c.nbmax + k];
+  if (with_grad) {
+    const int nt = nb * (nb + 1) / 2;
+    for (int t = threadIdx.x; t < nt; t += NTHREADS) {
+      const double* gp = c.gpart + ((long)s * c.ntmax + t) * NG;
+#pragma unroll
+      for (int k = 0; k < NG; ++k) v[k] += gp[k];
+    }
+  }
+  block_sum<NG + 1>(v, red);
+  if (threadIdx.x == 0) {
+    const double* th = c.theta + s * MAXP;
+    double f = 0.5 * c.quad[s] + v[NG] + 0.5 * N * 1.8378770664093453;
+    if (c.fail[s]) f = INFINITY;
+    c.fail[s] = 0;  // consumed: ready for the next evaluation
+    c.fout[s] = f;
+    double* go = c.gout + s * MAXP;
+    for (int d = 0; d < c.D; ++d) go[d] = 0.5 * v[d] / th[d];
+    go[c.D] = 0.5 * v[MAXD] / th[c.D];
+    go[c.D + 1] = 0.5 * v[MAXD + 1];
+  }
+}
+
+// ------------------------------------------------------------------------------------
+// Prediction.  Work item = (slot, pair of 64-wide blocks of prediction points).
+//   k_build_xp : cross-covariance tiles K(x_obs block k, x_pred block) -> scratch[item][k][t]
+//   k_predict2 : one CTA per item walks the row supertiles: A_I = sum_k X_{I,k} Kxp_k;
+//                column sums of A^2 over rows < N; row N -> -mean
+// ------------------------------------------------------------------------------------
+struct PredCtx {
+  int ppmax;                 // padded prediction points per slot
+  const double* pcoords;     // [S][MAXD][ppmax] prediction coords / coords_scale
+  const int* np;             // [S]
+  const int* item_slot;      // [n_items]
+  const int* item_pb;        // [n_items]  first 64-block of the pair
+  int n_items, item0;        // items of this wave: [item0, item0 + n_items)
+  double* scratch;           // [n_items][nbmax][2][4096]
+  double* fmean;             // [S][ppmax]
+  double* fvar;              // [S][ppmax]
+};
+
+// grid (nbmax, n_items), 256 threads
+__global__ void __launch_bounds__(256, 4) k_build_xp(SlotCtx c, PredCtx p) {
+  __shared__ double xo[MAXD * TB], xp[MAXD * 2 * TB];
+  const int item = p.item0 + blockIdx.y, k = blockIdx.x;
+  const int s = p.item_slot[item], pb = p.item_pb[item];
+  const int nb = c.nb[s];
+  if (k >= nb) return;
+  const int N = c.n[s], P = p.np[s];
+  const double* th = c.theta + s * MAXP;
+  stage_coords(xo, c.coords + (long)s * MAXD * c.npmax, c.npmax, c.D, th, k, N);
+  const double* ps = p.pcoords + (long)s * MAXD * p.ppmax;
+  for (int t = threadIdx.x; t < c.D * 2 * TB; t += blockDim.x) {
+    const int d = t / (2 * TB), m = t % (2 * TB), g = pb * TB + m;
+    xp[d * 2 * TB + m] = (g < P) ? ps[(long)d * p.ppmax + g] / th[d] : 0.0;
+  }
+  __syncthreads();
+  const double kvar = th[c.D];
+  const int kk = threadIdx.x >> 2, c0 = (threadIdx.x & 3) * 16, go = k * TB + kk;
+  double* out = p.scratch + ((long)blockIdx.y * c.nbmax + k) * 2 * TILE_ELEMS;
+  double xm[MAXD];
+#pragma unroll
+  for (int d = 0; d < MAXD; ++d) xm[d] = (d < c.D) ? xo[d * TB + kk] : 0.0;
+#pragma unroll
+  for (int t = 0; t < 2; ++t) {
+#pragma unroll
+    for (int cc = 0; cc < 16; cc += 2) {
+      double v[2];
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const int n = t * TB + c0 + cc + e;
+        double val = 0.0;
+        if (go < N && pb * TB + n < P) {
+          double r2 = 0.0;
+#pragma unroll
+          for (int d = 0; d < MAXD; ++d)
+            if (d < c.D) {
+              const double df = xm[d] - xp[d * 2 * TB + n];
+              r2 += df * df;
+            }
+          val = kern_value(c.kid, r2, kvar);
+        }
+        v[e] = val;
+      }
+      *reinterpret_cast<double2*>(out + t * TILE_ELEMS + swz(kk, c0 + cc)) = make_double2(v[0], v[1]);
+    }
+  }
+}
+
+// grid (n_items), NTHREADS threads
+__global__ void __launch_bounds__(NTHREADS, 1) k_predict2(SlotCtx c, PredCtx p) {
+  extern __shared__ __align__(128) double smem[];
+  double* meanv = smem + (SMEM2_ELEMS - G2_AUX);      // [128]
+  const int item = p.item0 + blockIdx.x;
+  const int s = p.item_slot[item], pb = p.item_pb[item];
+  const int N = c.n[s], nb = c.nb[s], nsr = (nb + 1) >> 1, P = p.np[s];
+  const bool two = (pb + 1) * TB < P;
+  const double* scr = p.scratch + (long)blockIdx.x * c.nbmax * 2 * TILE_ELEMS;
+  const double kvar = c.theta[s * MAXP + c.D];
+  Frag2 f;
+  double csq[4][2];
+#pragma unroll
+  for (int ni = 0; ni < 4; ++ni) csq[ni][0] = csq[ni][1] = 0.0;
+  const int bN = nb - 1, rN = N - bN * TB;
+  for (int I = 0; I < nsr; ++I) {
+    Acc2 acc;
+    acc.zero();
+    const int kend = (2 * I + 2 < nb) ? 2 * I + 2 : nb;
+    gemm2_pipeline<false, true>(
+        acc, smem, 0, kend,
+        [&](int k, int t) -> const double* {
+          return (2 * I + t < nb && k <= 2 * I + t) ? x_tile(c, s, 2 * I + t, k) : nullptr;
+        },
+        [&](int k, int t) -> const double* {
+          return (t == 0 || two) ? scr + ((long)k * 2 + t) * TILE_ELEMS : nullptr;
+        },
+        f);
+    const int ti = 2 * I + f.ta;
+    if (ti < nb && (f.tb == 0 || two)) {
+#pragma unroll
+      for (int mi = 0; mi < 8; ++mi) {
+        const int gi = ti * TB + f.row(mi);
+#pragma unroll
+        for (int ni = 0; ni < 4; ++ni) {
+          if (gi < N) {
+            csq[ni][0] += acc.c[mi][ni][0] * acc.c[mi][ni][0];
+            csq[ni][1] += acc.c[mi][ni][1] * acc.c[mi][ni][1];
+          } else if (ti == bN && f.row(mi) == rN) {
+            meanv[f.tb * TB + f.col(ni)] = -acc.c[mi][ni][0];
+            meanv[f.tb * TB + f.col(ni) + 1] = -acc.c[mi][ni][1];
+          }
+        }
+      }
+    }
+  }
+  // column sums: over q (lanes sharing r), then over the two warps (wm = 0, 1) of a column slab
+#pragma unroll
+  for (int ni = 0; ni < 4; ++ni)
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {
+      double v = csq[ni][e];
+      v += __shfl_xor_sync(0xffffffffu, v, 4);
+      v += __shfl_xor_sync(0xffffffffu, v, 8);
+      v += __shfl_xor_sync(0xffffffffu, v, 16);
+      csq[ni][e] = v;
+    }
+  double* part = smem;   // [2][128]: the pipeline ended with a barrier, the ring is idle
+  if (f.q == 0) {
+#pragma unroll
+    for (int ni = 0; ni < 4; ++ni) {
+      part[f.wm * 2 * TB + f.tb * TB + f.col(ni)] = csq[ni][0];
+      part[f.wm * 2 * TB + f.tb * TB + f.col(ni) + 1] = csq[ni][1];
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x < 2 * TB) {
+    const int n = threadIdx.x, gp = pb * TB + n;
+    if (gp < P) {
+      p.fvar[(long)s * p.ppmax + gp] = kvar - (part[n] + part[2 * TB + n]);
+      p.fmean[(long)s * p.ppmax + gp] = meanv[n];
+    }
+  }
+}
+
+// dense row-major kernel matrix for parity tests / HBM roofline of the kernel build (row K1)
+// K[i][j] = k(x_i, x2_j) (+ nvar on the diagonal when add_noise).  grid (ceil(n2/64), ceil(n1/16))
+__global__ void k_kernel_matrix(const double* __restrict__ X1, int n1, const double* __restrict__ X2, int n2,
+                                int D, int kid, const double* __restrict__ theta, int add_noise,
+                                double* __restrict__ K) {
+  __shared__ double x1s[16][MAXD], x2s[64][MAXD];
+  const int i0 = blockIdx.y * 16, j0 = blockIdx.x * 64;
+  const int tid = threadIdx.y * 64 + threadIdx.x;
+  for (int t = tid; t < 16 * D; t += 256) {
+    const int r = t / D, d = t % D;
+    x1s[r][d] = (i0 + r < n1) ? X1[(long)(i0 + r) * D + d] / theta[d] : 0.0;
+  }
+  for (int t = tid; t < 64 * D; t += 256) {
+    const int r = t / D, d = t % D;
+    x2s[r][d] = (j0 + r < n2) ? X2[(long)(j0 + r) * D + d] / theta[d] : 0.0;
+  }
+  __syncthreads();
+  const int j = j0 + threadIdx.x;
+  if (j >= n2) return;
+  for (int rr = threadIdx.y; rr < 16; rr += 4) {
+    const int i = i0 + rr;
+    if (i >= n1) break;
+    double r2 = 0.0;
+    for (int d = 0; d < D; ++d) {
+      const double df = x1s[rr][d] - x2s[threadIdx.x][d];
+      r2 += df * df;
+    }
+    double v = kern_value(kid, r2, theta[D]);
+    if (add_noise && i == j) v += theta[D + 1];
+    K[(long)i * n2 + j] = v;
+  }
+}
+
+// unpack packed swizzled lower tiles of one slot into a dense row-major (npad x npad) matrix.
+// which = 0: Lt as is; 1: X assembled through x_tile()
+__global__ void k_unpack_tiles(SlotCtx c, int s, int which, int nb, double* __restrict__ dense) {
+  const int i = blockIdx.y, j = blockIdx.x;
+  const int npad = nb * TB;
+  const double* src = nullptr;
+  if (j <= i) src = which ? x_tile(c, s, i, j) : tile_ptr(c.Lt + (long)s * c.tile_stride, i, j);
+  for (int t = threadIdx.x; t < TILE_ELEMS; t += blockDim.x) {
+    const int r = t >> 6, cc = t & 63;
+    dense[(long)(i * TB + r) * npad + j * TB + cc] = src ? src[swz(r, cc)] : 0.0;
+  }
+}
+
+}  // namespace gpsat
