@@ -72,6 +72,8 @@ _EXPORTS = {
                                      C.c_void_p, C.c_void_p]),
     "gpsat_gpr_predict": (C.c_int, [C.c_void_p, C.POINTER(Batch), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                     C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "gpsat_gpr_predict_cov": (C.c_int, [C.c_void_p, C.POINTER(Batch), C.c_void_p, C.c_void_p, C.c_int, C.c_void_p,
+                                        C.c_void_p, C.c_void_p]),
     "gpsat_debug_factor": (C.c_int, [C.c_void_p, C.POINTER(Batch), C.c_void_p, C.c_void_p, C.c_void_p,
                                      C.c_void_p]),
     "gpsat_launch_count": (C.c_longlong, [C.c_void_p]),

@@ -45,7 +45,7 @@ struct gpsat_handle {
   std::vector<cudaEvent_t> ev;
   size_t ev_used = 0;
   std::vector<double> ev_flops;  // N^3/3 summed over active slots for each recorded round
-  Buf Lt, Xt, Kt, quad, coords, yobs, ints, theta, logdet, gpart, fout, gout, states, order, pslot, pres, scratch, items;
+  Buf Lt, Xt, Kt, quad, abuf, coords, yobs, ints, theta, logdet, gpart, fout, gout, states, order, pslot, pres, scratch, items;
   int* host_ints = nullptr;  // pinned
   size_t host_ints_cap = 0;
   bool attrs_set = false;
@@ -105,7 +105,9 @@ extern "C" int gpsat_create(gpsat_handle** out, int device, size_t mem_budget_by
   CK(cudaFuncSetAttribute(k_trtri_pass1, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM2_BYTES));
   CK(cudaFuncSetAttribute(k_trtri_pass2, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM2_BYTES));
   CK(cudaFuncSetAttribute(k_lauum2, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM2_BYTES));
-  CK(cudaFuncSetAttribute(k_predict2, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM2_BYTES));
+  CK(cudaFuncSetAttribute(k_predict2<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM2_BYTES));
+  CK(cudaFuncSetAttribute(k_predict2<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM2_BYTES));
+  CK(cudaFuncSetAttribute(k_pred_cov, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM2_BYTES));
   *out = h;
   return 0;
 }
@@ -113,7 +115,7 @@ extern "C" int gpsat_create(gpsat_handle** out, int device, size_t mem_budget_by
 extern "C" int gpsat_destroy(gpsat_handle* h) {
   if (!h) return 0;
   cudaSetDevice(h->device);
-  Buf* bs[] = {&h->Lt, &h->Xt, &h->Kt, &h->quad, &h->coords, &h->yobs, &h->ints, &h->theta, &h->logdet, &h->gpart,
+  Buf* bs[] = {&h->Lt, &h->Xt, &h->Kt, &h->quad, &h->abuf, &h->coords, &h->yobs, &h->ints, &h->theta, &h->logdet, &h->gpart,
                &h->fout, &h->gout, &h->states, &h->order, &h->pslot, &h->pres, &h->scratch, &h->items};
   for (Buf* b : bs)
     if (b->p) cudaFree(b->p);
@@ -483,12 +485,13 @@ extern "C" int gpsat_gpr_predict(gpsat_handle* h, const gpsat_batch* b, const do
       p.scratch = (double*)h->scratch.p;
       p.fmean = (double*)h->pres.p;
       p.fvar = (double*)h->pres.p + (size_t)S * ppmax;
+      p.abuf = nullptr;
       const int nbm = nb_of(b->offsets_host, pl.order[first]);
       for (int i0 = 0; i0 < n_items; i0 += wave) {
         p.item0 = i0;
         p.n_items = std::min(wave, n_items - i0);
         k_build_xp<<<dim3(nbm, p.n_items), 256, 0, st>>>(w.c, p);
-        k_predict2<<<p.n_items, NTHREADS, SMEM2_BYTES, st>>>(w.c, p);
+        k_predict2<false><<<p.n_items, NTHREADS, SMEM2_BYTES, st>>>(w.c, p);
         h->launches += 2;
       }
       k_pred_scatter<<<S, NTHREADS, 0, st>>>(w.c, w.a, count, poff_dev, p.fmean, p.fvar, ppmax, fmean_dev,
@@ -496,6 +499,67 @@ extern "C" int gpsat_gpr_predict(gpsat_handle* h, const gpsat_batch* b, const do
       ++h->launches;
     }
   }
+  CK(cudaStreamSynchronize(st));
+  harvest_profile(h, true, false);
+  CK(cudaGetLastError());
+  return 0;
+}
+
+// full_cov=True branch of predict (gpflow_models.py:245-263) for ONE expert (the first of the batch)
+extern "C" int gpsat_gpr_predict_cov(gpsat_handle* h, const gpsat_batch* b, const double* theta_dev,
+                                     const double* pcoords_dev, int P, double* fmean_dev, double* fcov_dev,
+                                     void* stream) {
+  if (!h || !b || !theta_dev || !pcoords_dev || !fmean_dev || !fcov_dev || P < 1)
+    return fail(GPSAT_EINVAL, "bad argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  CK(cudaSetDevice(h->device));
+  gpsat_batch b1 = *b;
+  b1.n_experts = 1;
+  const int ppmax = (P + TB - 1) / TB * TB;
+  Plan pl;
+  int r = make_plan(h, &b1, pl);
+  if (r) return r;
+  Work w;
+  r = setup_work(h, &b1, pl, w, st);
+  if (r) return r;
+  const int n_items = (ppmax / TB + 1) / 2;
+  const size_t item_bytes = (size_t)pl.nbmax * 2 * TILE_BYTES;
+  if ((size_t)n_items * item_bytes * 2 > h->budget)
+    return fail(GPSAT_ENOMEM, "full covariance at this many prediction points does not fit the memory budget");
+  ENS(h->pslot, (size_t)MAXD * ppmax * 8 + 16 * sizeof(int) + MAXD * 8 + 2 * sizeof(long long));
+  ENS(h->pres, (size_t)2 * ppmax * 8);
+  ENS(h->scratch, (size_t)n_items * item_bytes);
+  ENS(h->abuf, (size_t)n_items * item_bytes);
+  ENS(h->items, (size_t)2 * n_items * sizeof(int));
+  double* pslot = (double*)h->pslot.p;
+  double* cs_dev = pslot + (size_t)MAXD * ppmax;
+  long long* poff_dev = (long long*)(cs_dev + MAXD);
+  int* np_dev = (int*)(poff_dev + 2);
+  BatchIn bi = make_batch_in(&b1, theta_dev, nullptr);
+  const long long poff[2] = {0, P};
+  CK(cudaMemcpyAsync(cs_dev, bi.coords_scale, MAXD * 8, cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(poff_dev, poff, sizeof(poff), cudaMemcpyHostToDevice, st));
+  std::vector<int> it(2 * n_items, 0);
+  for (int k = 0; k < n_items; ++k) it[n_items + k] = 2 * k;
+  CK(cudaMemcpyAsync(h->items.p, it.data(), it.size() * sizeof(int), cudaMemcpyHostToDevice, st));
+  CK(cudaStreamSynchronize(st));
+  TransformSpec tr = identity_transforms(b->D);
+  k_slot_init<<<pl.S, NTHREADS, 0, st>>>(w.c, w.a, bi, tr, 0, 1, 0);
+  r = run_round(h, w.c, pl.nbmax, true, false, st, 0.0);
+  if (r) return r;
+  k_pred_load<<<1, NTHREADS, 0, st>>>(w.a, 1, b->D, pcoords_dev, poff_dev, cs_dev, pslot, np_dev, ppmax);
+  PredCtx p;
+  p.ppmax = ppmax; p.pcoords = pslot; p.np = np_dev;
+  p.item_slot = (int*)h->items.p; p.item_pb = (int*)h->items.p + n_items;
+  p.n_items = n_items; p.item0 = 0;
+  p.scratch = (double*)h->scratch.p;
+  p.fmean = (double*)h->pres.p; p.fvar = (double*)h->pres.p + ppmax;
+  p.abuf = (double*)h->abuf.p;
+  k_build_xp<<<dim3(pl.nbmax, n_items), 256, 0, st>>>(w.c, p);
+  k_predict2<true><<<n_items, NTHREADS, SMEM2_BYTES, st>>>(w.c, p);
+  k_pred_cov<<<n_items * (n_items + 1) / 2, NTHREADS, SMEM2_BYTES, st>>>(w.c, p, fcov_dev);
+  h->launches += 6;
+  CK(cudaMemcpyAsync(fmean_dev, p.fmean, (size_t)P * 8, cudaMemcpyDeviceToDevice, st));
   CK(cudaStreamSynchronize(st));
   harvest_profile(h, true, false);
   CK(cudaGetLastError());

@@ -551,6 +551,7 @@ struct PredCtx {
   double* scratch;           // [n_items][nbmax][2][4096]
   double* fmean;             // [S][ppmax]
   double* fvar;              // [S][ppmax]
+  double* abuf;              // [n_items][nbmax][2][4096] A = L^-1 K_xp tiles (full_cov only) or nullptr
 };
 
 // grid (nbmax, n_items), 256 threads
@@ -602,6 +603,7 @@ __global__ void __launch_bounds__(256, 4) k_build_xp(SlotCtx c, PredCtx p) {
 }
 
 // grid (n_items), NTHREADS threads
+template <bool STORE_A>
 __global__ void __launch_bounds__(NTHREADS, 1) k_predict2(SlotCtx c, PredCtx p) {
   extern __shared__ __align__(128) double smem[];
   double* meanv = smem + (SMEM2_ELEMS - G2_AUX);      // [128]
@@ -630,6 +632,16 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_predict2(SlotCtx c, PredCtx p) 
         },
         f);
     const int ti = 2 * I + f.ta;
+    if (STORE_A && ti < nb) {   // rows >= N (augmented row, padding) must not enter A'A
+      Acc2 az = acc;
+#pragma unroll
+      for (int mi = 0; mi < 8; ++mi)
+        if (ti * TB + f.row(mi) >= N || !(f.tb == 0 || two)) {
+#pragma unroll
+          for (int ni = 0; ni < 4; ++ni) az.c[mi][ni][0] = az.c[mi][ni][1] = 0.0;
+        }
+      store_acc2(p.abuf + (((long)blockIdx.x * c.nbmax + ti) * 2 + f.tb) * TILE_ELEMS, az, f);
+    }
     if (ti < nb && (f.tb == 0 || two)) {
 #pragma unroll
       for (int mi = 0; mi < 8; ++mi) {
@@ -673,6 +685,46 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_predict2(SlotCtx c, PredCtx p) 
       p.fvar[(long)s * p.ppmax + gp] = kvar - (part[n] + part[2 * TB + n]);
       p.fmean[(long)s * p.ppmax + gp] = meanv[n];
     }
+  }
+}
+
+// full posterior covariance of one expert (slot 0): C(p, q) = K(x*_p, x*_q) - sum_k A_k,p' A_k,q.
+// grid (n_items (n_items + 1) / 2): lower 128x128 blocks, mirrored on store.  fcov: [P][P] row-major
+__global__ void __launch_bounds__(NTHREADS, 1) k_pred_cov(SlotCtx c, PredCtx p, double* __restrict__ fcov) {
+  extern __shared__ __align__(128) double smem[];
+  int bp, bq;
+  tri_decode(blockIdx.x, bp, bq);
+  const int s = 0, nb = c.nb[s], P = p.np[s];
+  Frag2 f;
+  Acc2 acc;
+  acc.zero();
+  const long istride = (long)c.nbmax * 2 * TILE_ELEMS;
+  gemm2_pipeline<true, true>(
+      acc, smem, 0, nb,
+      [&](int k, int t) -> const double* { return p.abuf + bp * istride + ((long)k * 2 + t) * TILE_ELEMS; },
+      [&](int k, int t) -> const double* { return p.abuf + bq * istride + ((long)k * 2 + t) * TILE_ELEMS; }, f);
+  const double* th = c.theta + s * MAXP;
+  const double* ps = p.pcoords + (long)s * MAXD * p.ppmax;
+  const double kvar = th[c.D];
+#pragma unroll
+  for (int mi = 0; mi < 8; ++mi) {
+    const int gp = (2 * bp + f.ta) * TB + f.row(mi);
+    if (gp >= P) continue;
+#pragma unroll
+    for (int ni = 0; ni < 4; ++ni)
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const int gq = (2 * bq + f.tb) * TB + f.col(ni) + e;
+        if (gq >= P) continue;
+        double r2 = 0.0;
+        for (int d = 0; d < c.D; ++d) {
+          const double df = ps[(long)d * p.ppmax + gp] / th[d] - ps[(long)d * p.ppmax + gq] / th[d];
+          r2 += df * df;
+        }
+        const double v = kern_value(c.kid, r2, kvar) - acc.c[mi][ni][e];
+        fcov[(long)gp * P + gq] = v;
+        fcov[(long)gq * P + gp] = v;
+      }
   }
 }
 

@@ -188,6 +188,21 @@ class Engine:
                                               _ptr(fobj), _stream_ptr(self.device)))
         return fmean, fvar, yvar, fobj
 
+    def predict_full_cov(self, batch: ExpertBatch, theta, pred_coords):
+        """posterior mean [P] and full covariance [P, P] of f* for the first expert of the batch"""
+        D = batch.D
+        th = self._theta_dev(theta, batch.n_experts, D)
+        pc = torch.as_tensor(np.ascontiguousarray(pred_coords, dtype=np.float64)).to(self.device)
+        if pc.ndim == 1:
+            pc = pc[:, None].contiguous()
+        P = pc.shape[0]
+        fmean = torch.empty(P, dtype=torch.float64, device=self.device)
+        fcov = torch.empty(P, P, dtype=torch.float64, device=self.device)
+        b = batch.c_struct()
+        _lib.check(self.lib.gpsat_gpr_predict_cov(self.h, C.byref(b), _ptr(th), _ptr(pc), P, _ptr(fmean), _ptr(fcov),
+                                                  _stream_ptr(self.device)))
+        return fmean, fcov
+
     # ---- K1 ----
     def kernel_matrix(self, X1, X2, theta, kernel="Matern32", coords_scale=None, add_noise=False):
         x1 = torch.as_tensor(np.ascontiguousarray(X1, dtype=np.float64)).to(self.device)

@@ -325,6 +325,17 @@ class LocalExpertOI:
         print(f"'run': {time.perf_counter() - t_run:.3f} seconds")
         return tables if return_tables else None
 
+    @classmethod
+    def run_from(cls, ref_oi, **run_kwargs):
+        """Batched run of an already configured reference ``GPSat.local_experts.LocalExpertOI`` instance
+        (the hook shown in INTEGRATION.md): its captured config dicts rebuild the driver."""
+        cfg = ref_oi.config
+        oi = cls(expert_loc_config=cfg.get("locations") or cfg.get("local_expert_locations"),
+                 data_config=cfg.get("data"), model_config=cfg.get("model"), pred_loc_config=cfg.get("pred_loc"))
+        if getattr(ref_oi, "expert_locs", None) is not None:
+            oi.expert_locs = ref_oi.expert_locs
+        return oi.run(**run_kwargs)
+
     def _device_name(self):
         import torch
         return torch.cuda.get_device_name(self.device)

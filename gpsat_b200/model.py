@@ -41,6 +41,9 @@ def _processor_name():
 class B200GPRModel:
     """Exact GP regression for one local expert, evaluated by hand-written sm_100a CUDA."""
 
+    # LocalExpertOI.run may hand the whole expert list to gpsat_b200.local_experts (INTEGRATION.md)
+    supports_batched_dispatch = True
+
     def __init__(self,
                  data: Optional[pd.DataFrame] = None,
                  coords_col: Union[str, List[str], None] = None,

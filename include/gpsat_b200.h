@@ -150,6 +150,12 @@ int gpsat_gpr_predict(gpsat_handle* h, const gpsat_batch* b, const double* theta
                       const double* pred_coords_dev, double* fmean_dev, double* fvar_dev,
                       double* yvar_dev, double* fobj_dev, void* stream);
 
+/* F1 with full_cov=True (gpflow_models.py:245-263) for the FIRST expert of the batch:
+ * fmean_dev[P], fcov_dev[P][P] (row-major posterior covariance of f*). */
+int gpsat_gpr_predict_cov(gpsat_handle* h, const gpsat_batch* b, const double* theta_dev,
+                          const double* pred_coords_dev, int P, double* fmean_dev, double* fcov_dev,
+                          void* stream);
+
 /* test hook: dense lower factor L and its inverse X (both (nb*64)^2 row-major, nb = n/64+1, of
  * the augmented matrix) of expert 0 of the batch at theta_dev. */
 int gpsat_debug_factor(gpsat_handle* h, const gpsat_batch* b, const double* theta_dev,
