@@ -22,7 +22,8 @@ import time
 import numpy as np
 import pandas as pd
 
-from .batched import ModelSpec, run_experts_host
+from .batched import ModelSpec
+from .distributed import run_experts_sharded
 from .model import B200GPRModel, get_model as _get_model
 from .params import PARAM_NAMES
 
@@ -301,10 +302,11 @@ class LocalExpertOI:
             theta_init, ok_load = self._load_theta(sub)
             if len(gdf) == 0:
                 table = np.zeros((len(table_cols), 1)) + np.inf     # nothing can be selected
-            res = run_experts_host(eng, spec, table, table_cols, obs_col, coords_col, refs, ref_cols,
-                                   self.local_select, pred_table=pred_tab, pred_cols=pred_cols,
-                                   max_dist=self.pred_max_dist, optimise=optimise, predict=predict,
-                                   min_obs=min_obs, theta_init=theta_init)
+            # one process per GPU: the expert list is sharded by N^3 cost and gathered once (distributed.py)
+            res = run_experts_sharded(eng, spec, table, table_cols, obs_col, coords_col, refs, ref_cols,
+                                      self.local_select, pred_table=pred_tab, pred_cols=pred_cols,
+                                      max_dist=self.pred_max_dist, optimise=optimise, predict=predict,
+                                      min_obs=min_obs, theta_init=theta_init)
             dt = time.perf_counter() - t0
             self._shape_tables(pieces, res, sub, members, ok_load, dt, optimise, predict, model_name, dev_name,
                                config_id, D)
@@ -320,7 +322,9 @@ class LocalExpertOI:
         tables[f"oi_config{table_suffix}"] = pd.DataFrame(
             {"idx": [config_id], "datetime": [datetime.datetime.now().strftime("%Y-%m-%d %H:%M:%S")],
              "config": [json.dumps(self.config, default=_json_default)]}).set_index("idx", drop=False)
-        if store_path is not None:
+        import torch.distributed as dist
+        is_writer = not (dist.is_available() and dist.is_initialized()) or dist.get_rank() == 0
+        if store_path is not None and is_writer:
             self._write(store_path, tables)
         print(f"'run': {time.perf_counter() - t_run:.3f} seconds")
         return tables if return_tables else None

@@ -1,0 +1,97 @@
+"""world_size-2 gloo tests (CPU) of the multi-GPU host logic: LPT partition, ragged gather and the merge
+back into global expert order.  No GPU and no engine: every rank fabricates its shard's results from a
+deterministic function of the global expert index, the merged result must equal the single-process one."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from gpsat_b200.distributed import _gather_padded, merge_shards, partition_lpt
+
+
+def test_partition_lpt_balances_and_is_deterministic():
+    rng = np.random.default_rng(0)
+    n = rng.integers(200, 8000, 500).astype(float)
+    cost = n ** 3
+    for world in (1, 2, 4, 8):
+        sh = partition_lpt(cost, world)
+        assert sorted(np.concatenate(sh).tolist()) == list(range(500))
+        loads = np.array([cost[s].sum() for s in sh])
+        assert loads.max() / loads.mean() < 1.02
+        assert all((np.diff(s) > 0).all() for s in sh)
+        sh2 = partition_lpt(cost.copy(), world)
+        assert all((a == b).all() for a, b in zip(sh, sh2))
+
+
+def _fake_result(gidx, D=3):
+    """what run_experts_host would return for the experts `gidx` (global indices)"""
+    gidx = np.asarray(gidx, dtype=np.int64)
+    num_obs = (gidx * 7) % 50
+    has_pred = (gidx % 11) != 0
+    too_few = has_pred & (num_obs < 3)
+    valid = has_pred & ~too_few
+    vidx = np.flatnonzero(valid)
+    g = gidx[vidx]
+    cnt = 1 + (g % 4)
+    poff = np.zeros(len(g) + 1, dtype=np.int64)
+    poff[1:] = np.cumsum(cnt)
+    rep = np.repeat(g, cnt)
+    within = np.concatenate([np.arange(c) for c in cnt]) if len(cnt) else np.zeros(0, dtype=np.int64)
+    return dict(num_obs=num_obs, has_pred=has_pred, too_few=too_few, valid=valid, valid_idx=vidx, n_valid=len(vidx),
+                theta=np.stack([g + 0.1 * k for k in range(D + 2)], axis=1).astype(float), fobj=-1.0 * g,
+                obs_mean=0.5 * g, status=(g % 3).astype(np.int32), nit=(g % 17).astype(np.int32),
+                nfev=(g % 19).astype(np.int32), pred_offsets=poff,
+                pred_coords=np.stack([rep + 0.0, within + 0.0, rep * 2.0], axis=1), fmean=rep + 0.25 * within,
+                fvar=rep * 3.0 + within, yvar=rep * 5.0 + within)
+
+
+def _worker(rank, world, port, E, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        cost = ((np.arange(E) * 37) % 101 + 1.0) ** 3
+        shards = partition_lpt(cost, world)
+        res = _fake_result(shards[rank])
+        keys = [k for k in res if k != "n_valid"]
+        gathered = {}
+        for k in keys:
+            t = torch.as_tensor(np.ascontiguousarray(res[k]))
+            if t.dtype == torch.bool:
+                t = t.to(torch.uint8)
+            gathered[k] = [g.numpy() for g in _gather_padded(t)]
+        parts = []
+        for r in range(world):
+            p = {k: gathered[k][r] for k in keys}
+            for k in ("has_pred", "too_few", "valid"):
+                p[k] = p[k].astype(bool)
+            p["n_valid"] = int(p["valid"].sum())
+            parts.append(p)
+        merged = merge_shards(shards, parts, E)
+        if rank == 0:
+            q.put({k: (v.tolist() if isinstance(v, np.ndarray) else v) for k, v in merged.items()})
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("E", [37, 5])
+def test_sharded_gather_matches_single_process(E):
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, E, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    merged = q.get(timeout=120)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    ref = _fake_result(np.arange(E))
+    for k, v in ref.items():
+        np.testing.assert_array_equal(np.asarray(merged[k]), np.asarray(v), err_msg=k)
