@@ -31,6 +31,11 @@ class Batch(C.Structure):
                 ("obs_mean_out_dev", C.c_void_p)]
 
 
+class SgprBatch(C.Structure):
+    _fields_ = [("data", Batch), ("z_offsets_host", C.c_void_p), ("z_offsets_dev", C.c_void_p),
+                ("z_coords_dev", C.c_void_p)]
+
+
 class Transforms(C.Structure):
     _fields_ = [("kind", C.c_int * MAXP), ("low", C.c_double * MAXP), ("high", C.c_double * MAXP),
                 ("trainable", C.c_int * MAXP)]
@@ -74,6 +79,12 @@ _EXPORTS = {
                                     C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "gpsat_gpr_predict_cov": (C.c_int, [C.c_void_p, C.POINTER(Batch), C.c_void_p, C.c_void_p, C.c_int, C.c_void_p,
                                         C.c_void_p, C.c_void_p]),
+    "gpsat_sgpr_eval": (C.c_int, [C.c_void_p, C.POINTER(SgprBatch), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "gpsat_sgpr_optimise": (C.c_int, [C.c_void_p, C.POINTER(SgprBatch), C.c_void_p, C.POINTER(Transforms),
+                                      C.POINTER(OptOptions), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                      C.c_void_p, C.c_void_p]),
+    "gpsat_sgpr_predict": (C.c_int, [C.c_void_p, C.POINTER(SgprBatch), C.c_void_p, C.c_void_p, C.c_void_p,
+                                     C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "gpsat_debug_factor": (C.c_int, [C.c_void_p, C.POINTER(Batch), C.c_void_p, C.c_void_p, C.c_void_p,
                                      C.c_void_p]),
     "gpsat_launch_count": (C.c_longlong, [C.c_void_p]),

@@ -11,6 +11,7 @@
 #include "engine.cuh"
 #include "selection.cuh"
 #include "microbench.cuh"
+#include "sgpr.cuh"
 
 using namespace gpsat;
 
@@ -46,6 +47,8 @@ struct gpsat_handle {
   size_t ev_used = 0;
   std::vector<double> ev_flops;  // N^3/3 summed over active slots for each recorded round
   Buf Lt, Xt, Kt, quad, abuf, coords, yobs, ints, theta, logdet, gpart, fout, gout, states, order, pslot, pres, scratch, items;
+  // sparse GPR: second tile pool (B = I + beta A'A'^T) and rectangular work matrices
+  Buf Lt2, Xt2, Kt2, quad2, logdet2, fail2, sg_mm, sg_mn, sg_vec, sg_scal, sg_gpart, sg_ints, sg_beta, sg_ymean, sg_zeros;
   int* host_ints = nullptr;  // pinned
   size_t host_ints_cap = 0;
   bool attrs_set = false;
@@ -108,6 +111,9 @@ extern "C" int gpsat_create(gpsat_handle** out, int device, size_t mem_budget_by
   CK(cudaFuncSetAttribute(k_predict2<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM2_BYTES));
   CK(cudaFuncSetAttribute(k_predict2<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM2_BYTES));
   CK(cudaFuncSetAttribute(k_pred_cov, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM2_BYTES));
+  CK(cudaFuncSetAttribute(k_tgemm<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM2_BYTES));
+  CK(cudaFuncSetAttribute(k_tgemm<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM2_BYTES));
+  CK(cudaFuncSetAttribute(k_tgemm<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM2_BYTES));
   *out = h;
   return 0;
 }
@@ -116,7 +122,9 @@ extern "C" int gpsat_destroy(gpsat_handle* h) {
   if (!h) return 0;
   cudaSetDevice(h->device);
   Buf* bs[] = {&h->Lt, &h->Xt, &h->Kt, &h->quad, &h->abuf, &h->coords, &h->yobs, &h->ints, &h->theta, &h->logdet, &h->gpart,
-               &h->fout, &h->gout, &h->states, &h->order, &h->pslot, &h->pres, &h->scratch, &h->items};
+               &h->fout, &h->gout, &h->states, &h->order, &h->pslot, &h->pres, &h->scratch, &h->items,
+               &h->Lt2, &h->Xt2, &h->Kt2, &h->quad2, &h->logdet2, &h->fail2, &h->sg_mm, &h->sg_mn, &h->sg_vec,
+               &h->sg_scal, &h->sg_gpart, &h->sg_ints, &h->sg_beta, &h->sg_ymean, &h->sg_zeros};
   for (Buf* b : bs)
     if (b->p) cudaFree(b->p);
   if (h->host_ints) cudaFreeHost(h->host_ints);
@@ -205,6 +213,7 @@ static int setup_work(gpsat_handle* h, const gpsat_batch* b, const Plan& pl, Wor
   }
   int* ip = (int*)h->ints.p;
   SlotCtx& c = w.c;
+  c.nvar_override = -1.0;
   c.S = S; c.D = b->D; c.kid = b->kernel_id; c.nbmax = pl.nbmax; c.npmax = pl.npmax; c.ntmax = pl.ntmax;
   c.tile_stride = (long)pl.ntmax * TILE_ELEMS;
   c.Lt = (double*)h->Lt.p; c.Xt = (double*)h->Xt.p; c.Kt = (double*)h->Kt.p; c.quad = (double*)h->quad.p;
@@ -242,13 +251,16 @@ static cudaEvent_t next_event(gpsat_handle* h) {
 }
 
 // one objective evaluation for all active slots.  nbm: max 64-blocks among active slots.
-static int run_round(gpsat_handle* h, const SlotCtx& c, int nbm, bool inverse, bool grad, cudaStream_t st,
-                     double flops_third) {
-  const bool prof = h->profiling;
+enum { RR_BUILD = 1, RR_INVERSE = 2, RR_LAUUM = 4, RR_TRACE = 8, RR_FINALIZE = 16, RR_PROFILE = 32 };
+static int run_round_flags(gpsat_handle* h, const SlotCtx& c, int nbm, int flags, cudaStream_t st,
+                           double flops_third) {
+  const bool prof = h->profiling && (flags & RR_PROFILE);
   const int nsr = (nbm + 1) / 2, ntm = nbm * (nbm + 1) / 2;
   if (prof) { cudaEventRecord(next_event(h), st); h->ev_flops.push_back(flops_third); }
-  k_build<<<dim3(ntm, c.S), 256, 0, st>>>(c);
-  ++h->launches;
+  if (flags & RR_BUILD) {
+    k_build<<<dim3(ntm, c.S), 256, 0, st>>>(c);
+    ++h->launches;
+  }
   for (int J = 0; J < nsr; ++J) {
     k_potrf_update2<<<dim3(nsr - J, c.S), NTHREADS, SMEM2_BYTES, st>>>(c, J);
     ++h->launches;
@@ -260,7 +272,7 @@ static int run_round(gpsat_handle* h, const SlotCtx& c, int nbm, bool inverse, b
   k_quad<<<c.S, NTHREADS, 0, st>>>(c);
   ++h->launches;
   if (prof) cudaEventRecord(next_event(h), st);
-  if (inverse) {
+  if (flags & RR_INVERSE) {
     for (int hh = 1; hh < nsr; hh *= 2) {
       const int nblk = (nsr + 2 * hh - 1) / (2 * hh);
       k_trtri_pass1<<<dim3(nblk * hh * hh, c.S), NTHREADS, SMEM2_BYTES, st>>>(c, hh);
@@ -269,17 +281,27 @@ static int run_round(gpsat_handle* h, const SlotCtx& c, int nbm, bool inverse, b
     }
   }
   if (prof) cudaEventRecord(next_event(h), st);
-  if (grad) {
+  if (flags & RR_LAUUM) {
     k_lauum2<<<dim3(nsr * (nsr + 1) / 2, c.S), NTHREADS, SMEM2_BYTES, st>>>(c);
+    ++h->launches;
+  }
+  if (flags & RR_TRACE) {
     k_grad_trace<<<dim3(ntm, c.S), 256, 0, st>>>(c);
-    h->launches += 2;
+    ++h->launches;
   }
   if (prof) cudaEventRecord(next_event(h), st);
-  k_finalize2<<<c.S, NTHREADS, 0, st>>>(c, grad ? 1 : 0);
-  ++h->launches;
+  if (flags & RR_FINALIZE) {
+    k_finalize2<<<c.S, NTHREADS, 0, st>>>(c, (flags & RR_TRACE) ? 1 : 0);
+    ++h->launches;
+  }
   if (prof) cudaEventRecord(next_event(h), st);
   CK(cudaGetLastError());
   return 0;
+}
+static int run_round(gpsat_handle* h, const SlotCtx& c, int nbm, bool inverse, bool grad, cudaStream_t st,
+                     double flops_third) {
+  return run_round_flags(h, c, nbm, RR_BUILD | RR_FINALIZE | RR_PROFILE | (inverse ? RR_INVERSE : 0) |
+                                        (grad ? (RR_LAUUM | RR_TRACE) : 0), st, flops_third);
 }
 
 static void harvest_profile(gpsat_handle* h, bool inverse, bool grad) {
@@ -565,6 +587,8 @@ extern "C" int gpsat_gpr_predict_cov(gpsat_handle* h, const gpsat_batch* b, cons
   CK(cudaGetLastError());
   return 0;
 }
+
+#include "sgpr_host.cuh"
 
 // ------------------------------------------------------------------------------------------
 // misc entry points

@@ -35,6 +35,7 @@ constexpr int SMEM2_BYTES = SMEM2_ELEMS * 8;
 
 struct SlotCtx {
   int S, D, kid, nbmax, npmax, ntmax;
+  double nvar_override;     // >= 0: diagonal term of k_build instead of theta's likelihood variance (SGPR jitter)
   long tile_stride;         // doubles per slot in Lt / Xt / Kt (= ntmax * TILE_ELEMS)
   double* Lt;               // [S][ntmax][4096] packed lower tiles: L_aug, later the off-diagonal part of X
   double* Xt;               // [S][ntmax][4096] diagonal 128-blocks of X = L_aug^-1 (+ scratch T)
@@ -98,7 +99,7 @@ __global__ void __launch_bounds__(256, 4) k_build(SlotCtx c) {
     yj[threadIdx.x] = (g < N) ? c.yobs[(long)s * c.npmax + g] : 0.0;
   }
   __syncthreads();
-  const double kvar = th[c.D], nvar = th[c.D + 1];
+  const double kvar = th[c.D], nvar = (c.nvar_override >= 0.0) ? c.nvar_override : th[c.D + 1];
   const int m = threadIdx.x >> 2, c0 = (threadIdx.x & 3) * 16, gi = i * TB + m;
   double* out = c.Kt + (long)s * c.tile_stride + tri_index(i, j) * TILE_ELEMS;
   double xm[MAXD];

@@ -203,6 +203,87 @@ class Engine:
                                                   _stream_ptr(self.device)))
         return fmean, fcov
 
+    # ---- SG1: sparse GPR ----
+    def make_sgpr_batch(self, batch: ExpertBatch, z_offsets, z_coords):
+        """Attach inducing points (CSR, raw coordinates) to a data batch."""
+        zoff_h = np.ascontiguousarray(np.asarray(z_offsets, dtype=np.int64))
+        assert len(zoff_h) == batch.n_experts + 1
+        zc = z_coords if isinstance(z_coords, torch.Tensor) else torch.as_tensor(
+            np.ascontiguousarray(z_coords, dtype=np.float64))
+        zc = zc.to(self.device, dtype=torch.float64).contiguous()
+        if zc.ndim == 1:
+            zc = zc[:, None].contiguous()
+        assert zc.shape == (int(zoff_h[-1]), batch.D)
+        return {"batch": batch, "zoff_host": zoff_h, "zoff_dev": torch.as_tensor(zoff_h).to(self.device),
+                "zcoords": zc}
+
+    @staticmethod
+    def _sgpr_struct(sb):
+        s = _lib.SgprBatch()
+        s.data = sb["batch"].c_struct()
+        s.z_offsets_host = sb["zoff_host"].ctypes.data
+        s.z_offsets_dev = sb["zoff_dev"].data_ptr()
+        s.z_coords_dev = sb["zcoords"].data_ptr()
+        return s
+
+    def sgpr_eval(self, sb, theta, grad=True):
+        """-ELBO [E] and d(-ELBO)/dtheta [E, D+2]."""
+        batch = sb["batch"]
+        E, D = batch.n_experts, batch.D
+        th = self._theta_dev(theta, E, D)
+        f = torch.empty(E, dtype=torch.float64, device=self.device)
+        g = torch.zeros(E, MAXP, dtype=torch.float64, device=self.device) if grad else None
+        s = self._sgpr_struct(sb)
+        _lib.check(self.lib.gpsat_sgpr_eval(self.h, C.byref(s), _ptr(th), _ptr(f), _ptr(g), _stream_ptr(self.device)))
+        return f, (g[:, :D + 2] if grad else None)
+
+    def sgpr_optimise(self, sb, theta0, kind, low, high, trainable, maxiter=10_000, maxfun=15_000, maxcor=10,
+                      maxls=20, ftol=2.220446049250313e-09, gtol=1e-5):
+        batch = sb["batch"]
+        E, D = batch.n_experts, batch.D
+        th0 = self._theta_dev(theta0, E, D)
+        tr = _lib.Transforms()
+        for p in range(D + 2):
+            tr.kind[p] = int(kind[p])
+            tr.low[p] = float(low[p])
+            tr.high[p] = float(high[p])
+            tr.trainable[p] = int(bool(trainable[p]))
+        oo = _lib.OptOptions(maxcor, maxiter, maxfun, maxls, ftol, gtol)
+        theta = torch.zeros(E, MAXP, dtype=torch.float64, device=self.device)
+        fobj = torch.empty(E, dtype=torch.float64, device=self.device)
+        status = torch.zeros(E, dtype=torch.int32, device=self.device)
+        nit = torch.zeros(E, dtype=torch.int32, device=self.device)
+        nfev = torch.zeros(E, dtype=torch.int32, device=self.device)
+        s = self._sgpr_struct(sb)
+        _lib.check(self.lib.gpsat_sgpr_optimise(self.h, C.byref(s), _ptr(th0), C.byref(tr), C.byref(oo), _ptr(theta),
+                                                _ptr(fobj), _ptr(status), _ptr(nit), _ptr(nfev),
+                                                _stream_ptr(self.device)))
+        return {"theta": theta[:, :D + 2], "theta_full": theta, "fobj": fobj, "status": status, "nit": nit,
+                "nfev": nfev}
+
+    def sgpr_predict(self, sb, theta, pred_offsets, pred_coords):
+        batch = sb["batch"]
+        E, D = batch.n_experts, batch.D
+        th = self._theta_dev(theta, E, D)
+        poff_host = np.ascontiguousarray(np.asarray(pred_offsets, dtype=np.int64))
+        assert len(poff_host) == E + 1
+        poff_dev = torch.as_tensor(poff_host).to(self.device)
+        pc = pred_coords if isinstance(pred_coords, torch.Tensor) else torch.as_tensor(
+            np.ascontiguousarray(pred_coords, dtype=np.float64))
+        pc = pc.to(self.device, dtype=torch.float64).contiguous()
+        if pc.ndim == 1:
+            pc = pc[:, None].contiguous()
+        P = int(poff_host[-1])
+        fmean = torch.empty(P, dtype=torch.float64, device=self.device)
+        fvar = torch.empty(P, dtype=torch.float64, device=self.device)
+        yvar = torch.empty(P, dtype=torch.float64, device=self.device)
+        fobj = torch.empty(E, dtype=torch.float64, device=self.device)
+        s = self._sgpr_struct(sb)
+        _lib.check(self.lib.gpsat_sgpr_predict(self.h, C.byref(s), _ptr(th), C.c_void_p(poff_host.ctypes.data),
+                                               _ptr(poff_dev), _ptr(pc), _ptr(fmean), _ptr(fvar), _ptr(yvar),
+                                               _ptr(fobj), _stream_ptr(self.device)))
+        return fmean, fvar, yvar, fobj
+
     # ---- K1 ----
     def kernel_matrix(self, X1, X2, theta, kernel="Matern32", coords_scale=None, add_noise=False):
         x1 = torch.as_tensor(np.ascontiguousarray(X1, dtype=np.float64)).to(self.device)

@@ -156,6 +156,31 @@ int gpsat_gpr_predict_cov(gpsat_handle* h, const gpsat_batch* b, const double* t
                           const double* pred_coords_dev, int P, double* fmean_dev, double* fcov_dev,
                           void* stream);
 
+/* SG1: sparse GPR (GPflowSGPRModel, gpflow_models.py:666-901; gpflow.models.SGPR with Kuu jitter 1e-6).
+ * `data` is the usual CSR batch (N observations per expert); the inducing points are a second CSR
+ * (M per expert, raw coordinates, fixed: train_inducing_points=False is the reference's default). */
+typedef struct {
+  gpsat_batch data;
+  const long long* z_offsets_host;   /* [E+1] */
+  const long long* z_offsets_dev;    /* [E+1] */
+  const double* z_coords_dev;        /* [sumM][D] */
+} gpsat_sgpr_batch;
+
+/* f_dev[E] = -ELBO (the training loss gpflow minimises; get_objective_function_value() returns +ELBO,
+ * gpflow_models.py:860-862) and grad_dev[E][GPSAT_MAXP] = d(-ELBO)/d(theta) (optional). */
+int gpsat_sgpr_eval(gpsat_handle* h, const gpsat_sgpr_batch* sb, const double* theta_dev, double* f_dev,
+                    double* grad_dev, void* stream);
+/* optimise_parameters(train_inducing_points=False) (gpflow_models.py:864-901) */
+int gpsat_sgpr_optimise(gpsat_handle* h, const gpsat_sgpr_batch* sb, const double* theta0_dev,
+                        const gpsat_transforms* tr, const gpsat_opt_options* opts, double* theta_out_dev,
+                        double* fobj_out_dev, int* status_out_dev, int* nit_out_dev, int* nfev_out_dev,
+                        void* stream);
+/* predict (gpflow SGPR.predict_f / predict_y); fobj_dev (optional) gets -ELBO at theta */
+int gpsat_sgpr_predict(gpsat_handle* h, const gpsat_sgpr_batch* sb, const double* theta_dev,
+                       const long long* pred_offsets_host, const long long* pred_offsets_dev,
+                       const double* pred_coords_dev, double* fmean_dev, double* fvar_dev, double* yvar_dev,
+                       double* fobj_dev, void* stream);
+
 /* test hook: dense lower factor L and its inverse X (both (nb*64)^2 row-major, nb = n/64+1, of
  * the augmented matrix) of expert 0 of the batch at theta_dev. */
 int gpsat_debug_factor(gpsat_handle* h, const gpsat_batch* b, const double* theta_dev,

@@ -269,9 +269,11 @@ class OracleGPRModel:
         self.opt_result = None
 
     # ---- params ----
+    HYPERS = ["lengthscales", "kernel_variance", "likelihood_variance"]
+
     @property
     def param_names(self):
-        return ["lengthscales", "kernel_variance", "likelihood_variance"]
+        return list(self.HYPERS)
 
     def get_lengthscales(self):
         return self.ls.copy()
@@ -379,7 +381,7 @@ class OracleGPRModel:
     def _transforms_flat(self):
         """per-element (kind, low, high) arrays over [ls..., kvar, nvar]."""
         kind, low, high = [], [], []
-        for nm in self.param_names:
+        for nm in self.HYPERS:
             t = self.tr[nm]
             n = len(self.ls) if nm == "lengthscales" else 1
             kind += [t.kind] * n
@@ -389,7 +391,7 @@ class OracleGPRModel:
 
     def unconstrained(self):
         return np.concatenate([self.tr[nm].inv(np.atleast_1d(getattr(self, f"get_{nm}")()))
-                               for nm in self.param_names])
+                               for nm in self.HYPERS])
 
     def objective_u(self, u_free, free_mask, u_all):
         """f(u), df/du on the trainable subset (what gpflow.optimizers.Scipy hands scipy)."""
@@ -398,7 +400,7 @@ class OracleGPRModel:
         D = len(self.ls)
         th, dth = [], []
         off = 0
-        for nm in self.param_names:
+        for nm in self.HYPERS:
             n = D if nm == "lengthscales" else 1
             th.append(self.tr[nm].fwd(u[off:off + n]))
             dth.append(self.tr[nm].dfwd(u[off:off + n]))
@@ -436,7 +438,7 @@ class OracleGPRModel:
         self.opt_result = res
         u_all[free] = xf
         off = 0
-        for nm in self.param_names:
+        for nm in self.HYPERS:
             n = D if nm == "lengthscales" else 1
             v = self.tr[nm].fwd(u_all[off:off + n])
             if nm == "lengthscales":
