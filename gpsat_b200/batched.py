@@ -36,6 +36,7 @@ class ModelSpec:
     fixed_params: Sequence[str] = field(default_factory=list)
     max_iter: int = 10_000
     opt_kwargs: dict = field(default_factory=dict)   # ftol / gtol / maxcor / maxls / maxfun overrides
+    num_inducing_points: Optional[int] = None        # set -> sparse GPR (GPflowSGPRModel, gpflow_models.py:666-901)
 
     @staticmethod
     def from_model_config(model_config: dict) -> "ModelSpec":
@@ -43,12 +44,16 @@ class ModelSpec:
         ip = dict(model_config.get("init_params") or {})
         kk = dict(ip.pop("kernel_kwargs", None) or {})
         ok = dict(model_config.get("optim_kwargs") or {})
+        sparse = str(model_config.get("oi_model", "")).endswith("SGPRModel") or "num_inducing_points" in ip
+        nip = ip.pop("num_inducing_points", 500) if sparse else None
+        assert not ok.pop("train_inducing_points", False), "inducing points are kept fixed (the reference's default)"
         spec = ModelSpec(kernel=ip.pop("kernel", "Matern32"), coords_scale=ip.pop("coords_scale", None),
                          obs_scale=ip.pop("obs_scale", None) or 1.0, obs_mean=ip.pop("obs_mean", None),
                          lengthscales=kk.pop("lengthscales", None), kernel_variance=kk.pop("variance", 1.0),
                          constraints=model_config.get("constraints"),
                          fixed_params=list(ok.pop("fixed_params", None) or []),
                          max_iter=int(ok.pop("max_iter", 10_000)), opt_kwargs=ok)
+        spec.num_inducing_points = nip
         nv = ip.pop("noise_variance", None)
         if nv is not None:
             spec.likelihood_variance = float(nv)
@@ -146,11 +151,21 @@ def run_experts(eng: Engine, spec: ModelSpec, table_dev: torch.Tensor, table_col
     else:
         th = torch.as_tensor(theta_init, dtype=torch.float64, device=dev).index_select(0, vidx)
         theta0 = _move_within_tol(th, spec, hp)
+    # ---- SG1: inducing points (gpflow_models.py:809-819), same global-RNG draws as the sequential loop ----
+    sparse = spec.num_inducing_points is not None
+    sb = None
+    if sparse:
+        zoff_h, zidx = inducing_rows(ooff_h, spec.num_inducing_points)
+        zc = coords.index_select(0, torch.as_tensor(zidx, device=dev))
+        sb = eng.make_sgpr_batch(batch, zoff_h, zc)
+        csd = torch.as_tensor(np.broadcast_to(np.asarray(cs, dtype=np.float64).ravel(), (D,)).copy(), device=dev)
+        out.update(z_offsets=torch.as_tensor(zoff_h), inducing_points=zc / csd)
     # ---- P1 ----
     if optimise:
         ok = dict(spec.opt_kwargs)
-        res = eng.optimise(batch, theta0, kind, low, high, hp.trainable_mask(spec.fixed_params),
-                           maxiter=spec.max_iter, **ok)
+        opt = eng.sgpr_optimise if sparse else eng.optimise
+        res = opt(sb if sparse else batch, theta0, kind, low, high, hp.trainable_mask(spec.fixed_params),
+                  maxiter=spec.max_iter, **ok)
         theta = res["theta_full"]
         out.update(status=res["status"], nit=res["nit"], nfev=res["nfev"])
     else:
@@ -166,12 +181,39 @@ def run_experts(eng: Engine, spec: ModelSpec, table_dev: torch.Tensor, table_col
             out["pred_idx"] = pidx
         else:
             pcoords = refs_v[:, [ref_cols.index(c) for c in coords_col]].contiguous()
-        fm, fv, yv, fo = eng.predict(batch, theta, poff_h, pcoords, pred_offsets_dev=poff)
+        if sparse:
+            fm, fv, yv, fo = eng.sgpr_predict(sb, theta, poff_h, pcoords)
+        else:
+            fm, fv, yv, fo = eng.predict(batch, theta, poff_h, pcoords, pred_offsets_dev=poff)
         out.update(pred_offsets=poff, pred_coords=pcoords, fmean=fm, fvar=fv, yvar=yv, fobj=fo)
     else:
-        fo, _ = eng.eval(batch, theta, grad=False)
+        fo, _ = eng.sgpr_eval(sb, theta, grad=False) if sparse else eng.eval(batch, theta, grad=False)
         out["fobj"] = fo
+    if sparse:      # get_objective_function_value() of the sparse model is +ELBO (gpflow_models.py:860-862)
+        out["fobj"] = -out["fobj"]
     return out
+
+
+def inducing_rows(obs_offsets_host: np.ndarray, num_inducing_points: int):
+    """Row indices (into the concatenated local data) of every expert's inducing points.
+
+    The reference shuffles a copy of the expert's coordinates with numpy's GLOBAL RNG and keeps the
+    first M rows (all rows when N < M).  Shuffling an index vector consumes exactly the same random
+    draws, so with the same seed and expert order this reproduces the reference's choice.
+    """
+    zoff = [0]
+    idx = []
+    for e in range(len(obs_offsets_host) - 1):
+        o0, n = int(obs_offsets_host[e]), int(obs_offsets_host[e + 1] - obs_offsets_host[e])
+        if n < num_inducing_points:
+            sel = np.arange(n, dtype=np.int64)
+        else:
+            perm = np.arange(n, dtype=np.int64)
+            np.random.shuffle(perm)
+            sel = perm[:num_inducing_points]
+        idx.append(o0 + sel)
+        zoff.append(zoff[-1] + len(sel))
+    return np.array(zoff, dtype=np.int64), np.concatenate(idx) if idx else np.zeros(0, dtype=np.int64)
 
 
 def _move_within_tol(theta: torch.Tensor, spec: ModelSpec, hp: HyperParams) -> torch.Tensor:

@@ -24,7 +24,7 @@ import pandas as pd
 
 from .batched import ModelSpec
 from .distributed import run_experts_sharded
-from .model import B200GPRModel, get_model as _get_model
+from .model import B200GPRModel, B200SGPRModel, get_model as _get_model
 from .params import PARAM_NAMES
 
 _COMP = {">=": np.greater_equal, ">": np.greater, "==": np.equal, "<": np.less, "<=": np.less_equal,
@@ -172,10 +172,11 @@ class LocalExpertOI:
             self.model = getattr(importlib.import_module(oi_model["path_to_model"]), oi_model["model_name"])
         else:
             self.model = oi_model
-        assert self.model is B200GPRModel, "the batched driver dispatches B200GPRModel only"
+        assert self.model in (B200GPRModel, B200SGPRModel), "the batched driver dispatches B200GPRModel / B200SGPRModel"
         assert replacement_threshold is None, "replacement models are not supported by the batched dispatch"
         self.model_config = dict(init_params=init_params or {}, constraints=constraints,
-                                 optim_kwargs=optim_kwargs or {})
+                                 optim_kwargs=optim_kwargs or {},
+                                 oi_model="B200SGPRModel" if self.model is B200SGPRModel else "B200GPRModel")
         self.pred_kwargs = pred_kwargs or {}
         assert not self.pred_kwargs.get("full_cov", False), "full_cov predictions are not stored by run()"
         self.load_params_config = load_params
@@ -407,6 +408,15 @@ class LocalExpertOI:
             if "likelihood_variance" in names:
                 pieces.setdefault("likelihood_variance", []).append((first, pd.DataFrame(
                     {"_dim_0": 0, "likelihood_variance": th[:, D + 1], "_pos_": pos[k]}, index=midx(ref[k]))))
+            if "inducing_points" in res and (self.params_to_store is None or "inducing_points" in names):
+                zo = res["z_offsets"]
+                zc = res["inducing_points"]
+                mk = np.diff(zo)[vpos[k]]
+                rows = np.concatenate([np.arange(zo[v], zo[v + 1]) for v in vpos[k]])
+                d0 = np.concatenate([np.repeat(np.arange(m), D) for m in mk])
+                pieces.setdefault("inducing_points", []).append((first, pd.DataFrame(
+                    {"_dim_0": d0, "_dim_1": np.tile(np.arange(D), len(rows)), "inducing_points": zc[rows].ravel(),
+                     "_pos_": np.repeat(pos[k], mk * D)}, index=midx(np.repeat(ref[k], mk * D, axis=0)))))
         # preds
         if predict:
             poff = res["pred_offsets"]

@@ -264,6 +264,8 @@ def get_model(name):
     """Name lookup in the style of GPSat.models.get_model (models/__init__.py:3-26)."""
     if name in ("B200GPRModel", "GPflowGPRModel"):
         return B200GPRModel
+    if name in ("B200SGPRModel", "GPflowSGPRModel"):
+        return B200SGPRModel
     raise NotImplementedError(f"model: {name} is not implemented by gpsat_b200")
 
 
@@ -291,8 +293,102 @@ def register(gpsat_module=None):
         def wrapped(name, _orig=orig):
             if name == "B200GPRModel":
                 return B200GPRModel
+            if name == "B200SGPRModel":
+                return B200SGPRModel
             return _orig(name)
 
         wrapped._gpsat_b200 = True
         m.get_model = wrapped
     return [m.__name__ for m in mods]
+
+
+class B200SGPRModel(B200GPRModel):
+    """Sparse GPR with M inducing points: drop-in for ``GPflowSGPRModel`` (gpflow_models.py:666-901).
+
+    Inducing points follow the reference exactly: all data if N < M, else the first M rows of a
+    ``np.random.shuffle`` of a copy of the (scaled) coordinates -- reproducible only if the caller
+    seeds numpy's global RNG, like the reference (gpflow_models.py:809-819).
+    ``get_objective_function_value`` returns +ELBO (gpflow_models.py:860-862).
+    """
+
+    def __init__(self, data=None, coords_col=None, obs_col=None, coords=None, obs=None, coords_scale=None,
+                 obs_scale=None, obs_mean=None, verbose=True, *, kernel="Matern32", num_inducing_points=500,
+                 kernel_kwargs=None, mean_function=None, mean_func_kwargs=None, noise_variance=None,
+                 likelihood=None, **kwargs):
+        super().__init__(data=data, coords_col=coords_col, obs_col=obs_col, coords=coords, obs=obs,
+                         coords_scale=coords_scale, obs_scale=obs_scale, obs_mean=obs_mean, verbose=verbose,
+                         kernel=kernel, kernel_kwargs=kernel_kwargs, mean_function=mean_function,
+                         mean_func_kwargs=mean_func_kwargs, noise_variance=noise_variance, likelihood=likelihood,
+                         **kwargs)
+        assert num_inducing_points is not None, "num_inducing_points is None, must be specified for SGPR"
+        if len(self.coords) < num_inducing_points:
+            if verbose:
+                print("number of inducing points is more than number of data points, "
+                      "setting inducing points to data points...")
+            self.inducing_points = self.coords
+        else:
+            X = self.coords.copy()
+            np.random.shuffle(X)
+            self.inducing_points = X[:num_inducing_points]
+        self._sbatch = None
+
+    @property
+    def param_names(self) -> list:
+        return list(PARAM_NAMES) + ["inducing_points"]
+
+    def get_inducing_points(self) -> np.ndarray:
+        return np.array(self.inducing_points)
+
+    def set_inducing_points(self, inducing_points):
+        self.inducing_points = np.array(inducing_points, dtype=np.float64)
+        self._sbatch = None
+
+    def _get_sbatch(self):
+        if self._sbatch is None:
+            eng = self._engine()
+            Z = np.ascontiguousarray(self.inducing_points, dtype=np.float64)
+            self._sbatch = eng.make_sgpr_batch(self._get_batch(), np.array([0, len(Z)], dtype=np.int64), Z)
+        return self._sbatch
+
+    def get_objective_function_value(self):
+        f, _ = self._engine().sgpr_eval(self._get_sbatch(), self._hp.theta(), grad=False)
+        return -float(f[0])
+
+    def optimise_parameters(self, train_inducing_points=False, max_iter=10_000, fixed_params=None, **opt_kwargs):
+        assert not train_inducing_points, "B200SGPRModel keeps the inducing points fixed (the reference's default)"
+        t0 = time.perf_counter()
+        kind, low, high = self._hp.transforms()
+        options = dict(opt_kwargs.pop("options", None) or {})
+        options.update({k: opt_kwargs.pop(k) for k in ("ftol", "gtol", "maxcor", "maxls", "maxfun") if k in opt_kwargs})
+        assert opt_kwargs.pop("method", "L-BFGS-B") == "L-BFGS-B", "only L-BFGS-B is implemented"
+        assert not opt_kwargs, f"unsupported optimiser arguments: {list(opt_kwargs)}"
+        res = self._engine().sgpr_optimise(self._get_sbatch(), self._hp.theta(), kind, low, high,
+                                           self._hp.trainable_mask(fixed_params),
+                                           maxiter=int(options.pop("maxiter", max_iter)), **options)
+        self._hp.set_theta(res["theta"][0].cpu().numpy())
+        status = int(res["status"][0])
+        from ._lib import OPT_STATUS
+        self.opt_info = {"status": status, "message": OPT_STATUS[status], "nit": int(res["nit"][0]),
+                         "nfev": int(res["nfev"][0]), "fun": float(res["fobj"][0])}
+        if self.verbose:
+            print(f"'optimise_parameters': {time.perf_counter() - t0:.3f} seconds")
+        return status in (1, 2)
+
+    def predict(self, coords, full_cov=False, apply_scale=True) -> Dict[str, np.ndarray]:
+        assert not full_cov, "full_cov is not implemented for the sparse model"
+        if isinstance(coords, (pd.Series, pd.DataFrame)):
+            coords = coords[self.coords_col].values if self.coords_col is not None else coords.values
+        if isinstance(coords, list):
+            coords = np.array(coords)
+        if len(coords.shape) == 1:
+            coords = coords[None, :]
+        coords = coords.astype(self.coords.dtype)
+        if apply_scale:
+            coords = coords / self.coords_scale
+        P = len(coords)
+        fm, fv, yv, _ = self._engine().sgpr_predict(self._get_sbatch(), self._hp.theta(),
+                                                    np.array([0, P], dtype=np.int64), np.ascontiguousarray(coords))
+        out = {"f*": fm.cpu().numpy(), "f*_var": fv.cpu().numpy(), "y_var": yv.cpu().numpy()}
+        f_bar = self.obs_mean[:, 0]
+        out["f_bar"] = np.repeat(f_bar, P) if len(f_bar) != P else f_bar
+        return out

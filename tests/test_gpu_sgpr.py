@@ -135,3 +135,74 @@ def test_kat2_sgpr_all_points_equals_sklearn(eng, golden_dir):
     fm, fv, _, _ = eng.sgpr_predict(sb, th, np.array([0, 1]), g["x_test"])
     assert abs(fm.item() - float(g["pred_mean"][0])) < 1e-4
     assert abs(fv.item() - float(g["pred_var"][0])) < 1e-4
+
+
+def test_sgpr_through_the_driver_matches_sequential_oracle(eng):
+    """LocalExpertOI with oi_model = B200SGPRModel vs the oracle loop with OracleSGPRModel: same inducing points
+    (same numpy seed and expert order), ELBO / hyper-parameters / predictions within tolerance."""
+    import pandas as pd
+    from gpsat_b200.local_experts import LocalExpertOI
+    from oracle.local_expert_oi import run_local_expert_oi
+    rng = np.random.default_rng(11)
+    n = 5000
+    df = pd.DataFrame({"x": rng.uniform(-5e5, 5e5, n), "y": rng.uniform(-5e5, 5e5, n),
+                       "t": rng.integers(18322, 18331, n).astype(float)})
+    df["z"] = 0.1 * np.sin(df["x"] / 2e5) + 0.05 * np.cos(df["y"] / 1.5e5) + rng.normal(0, 0.05, n)
+    eloc = pd.DataFrame({"x": [0.0, 2e5, -1e5], "y": [0.0, -1e5, 2e5], "t": [18326.0] * 3})
+    gx, gy = np.meshgrid(np.arange(-2e5, 2e5 + 1, 5e4), np.arange(-2e5, 2e5 + 1, 5e4))
+    ploc = pd.DataFrame({"x": gx.ravel(), "y": gy.ravel()})
+    data = {"data_source": df, "obs_col": "z", "coords_col": ["x", "y", "t"],
+            "local_select": [{"col": "t", "comp": "<=", "val": 4}, {"col": "t", "comp": ">=", "val": -4},
+                             {"col": ["x", "y"], "comp": "<", "val": 200_000}]}
+    model = {"oi_model": "B200SGPRModel",
+             "init_params": {"coords_scale": [50000, 50000, 1], "num_inducing_points": 80, "obs_mean": "local"},
+             "constraints": {"lengthscales": {"low": [1e-8] * 3, "high": [600000, 600000, 9]},
+                             "likelihood_variance": {"low": 0.00125, "high": 0.01}}}
+    pred = {"method": "from_dataframe", "df": ploc, "max_dist": 100_000}
+    np.random.seed(42)
+    tabs = LocalExpertOI(expert_loc_config={"source": eloc}, data_config=data, model_config=model,
+                         pred_loc_config=pred).run(store_path=None)
+    np.random.seed(42)
+    ref_tabs, per = run_local_expert_oi(eloc, data, {k: v for k, v in model.items() if k != "oi_model"}, pred,
+                                        model_cls=sgpr.OracleSGPRModel)
+    assert set(ref_tabs) <= set(tabs)
+    ip, ipr = tabs["inducing_points"], ref_tabs["inducing_points"]
+    assert list(ip.columns) == list(ipr.columns) and ip.index.equals(ipr.index)
+    np.testing.assert_array_equal(ip["_dim_0"].values, ipr["_dim_0"].values)
+    np.testing.assert_array_equal(ip["_dim_1"].values, ipr["_dim_1"].values)
+    np.testing.assert_allclose(ip["inducing_points"].values, ipr["inducing_points"].values, rtol=1e-15)
+    rd, rrd = tabs["run_details"], ref_tabs["run_details"]
+    np.testing.assert_array_equal(rd["num_obs"].values, rrd["num_obs"].values)
+    f, fr = rd["objective_value"].values, rrd["objective_value"].values       # +ELBO for the sparse model
+    assert (f >= fr - 1e-6 * np.abs(fr)).all(), (f, fr)
+    np.testing.assert_array_equal(rd["optimise_success"].values, rrd["optimise_success"].values)
+    p, pr = tabs["preds"], ref_tabs["preds"]
+    assert p.index.equals(pr.index)
+    for c in ("f*", "f*_var", "y_var"):
+        np.testing.assert_allclose(p[c].values, pr[c].values, rtol=1e-4, atol=1e-4 * np.abs(pr[c].values).max())
+    np.testing.assert_allclose(p["f_bar"].values, pr["f_bar"].values, rtol=1e-12)
+
+
+def test_sgpr_model_class(eng):
+    from gpsat_b200.model import B200SGPRModel
+    rng = np.random.default_rng(21)
+    X, y, cs = _synth(rng, 220)
+    kw = dict(coords=X, obs=y, coords_scale=list(cs), obs_mean="local", num_inducing_points=60)
+    np.random.seed(5)
+    m = B200SGPRModel(verbose=False, **kw)
+    np.random.seed(5)
+    o = sgpr.OracleSGPRModel(**kw)
+    np.testing.assert_array_equal(m.get_inducing_points(), o.get_inducing_points())
+    for mod in (m, o):
+        mod.set_parameters(lengthscales=[3.0, 4.0, 5.0], kernel_variance=0.02, likelihood_variance=0.004)
+    assert abs(m.get_objective_function_value() - o.get_objective_function_value()) <= \
+        1e-8 * abs(o.get_objective_function_value())
+    Xp = np.column_stack([rng.uniform(-2e5, 2e5, (30, 2)), np.full(30, 18326.0)])
+    p, pr = m.predict(Xp), o.predict(Xp)
+    for k in ("f*", "f*_var", "y_var", "f_bar"):
+        np.testing.assert_allclose(p[k], pr[k], rtol=1e-6, atol=1e-9)
+    assert m.optimise_parameters(fixed_params=["likelihood_variance"]) == o.optimise_parameters(
+        fixed_params=["likelihood_variance"])
+    assert m.get_likelihood_variance() == 0.004
+    assert m.get_objective_function_value() >= o.get_objective_function_value() - 1e-6 * abs(
+        o.get_objective_function_value())
