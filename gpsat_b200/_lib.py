@@ -31,6 +31,10 @@ class Batch(C.Structure):
                 ("obs_mean_out_dev", C.c_void_p)]
 
 
+class CellGrid(C.Structure):
+    _fields_ = [("x0", C.c_double), ("y0", C.c_double), ("cell", C.c_double), ("ncx", C.c_int), ("ncy", C.c_int)]
+
+
 class SgprBatch(C.Structure):
     _fields_ = [("data", Batch), ("z_offsets_host", C.c_void_p), ("z_offsets_dev", C.c_void_p),
                 ("z_coords_dev", C.c_void_p)]
@@ -65,6 +69,11 @@ _EXPORTS = {
                                      C.c_void_p, C.c_void_p]),
     "gpsat_select_fill": (C.c_int, [C.POINTER(SelSpec), C.c_void_p, C.c_longlong, C.c_void_p, C.c_int, C.c_int,
                                     C.c_void_p, C.c_void_p, C.c_void_p]),
+    "gpsat_bucket_build": (C.c_int, [C.POINTER(SelSpec), C.POINTER(CellGrid), C.c_void_p, C.c_longlong, C.c_int,
+                                     C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "gpsat_select_bucket": (C.c_int, [C.POINTER(SelSpec), C.POINTER(CellGrid), C.c_void_p, C.c_longlong, C.c_void_p,
+                                      C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p,
+                                      C.c_void_p, C.c_void_p]),
     "gpsat_gather_rows": (C.c_int, [C.c_void_p, C.c_longlong, C.c_void_p, C.c_longlong, C.c_int,
                                     C.POINTER(C.c_int), C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
     "gpsat_gather_pred": (C.c_int, [C.c_void_p, C.c_longlong, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p,

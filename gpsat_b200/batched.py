@@ -114,12 +114,16 @@ def run_experts(eng: Engine, spec: ModelSpec, table_dev: torch.Tensor, table_col
                                     "rcols": [ref_cols.index(c) for c in found], "val": max_dist}])
         else:
             pspec = make_sel_spec([])
-        pcounts = eng.select_count(pspec, pred_table_dev, refs_dev)
+        pbk = eng.build_buckets(pspec, pred_table_dev)
+        pcounts = eng.select_count_bucketed(pspec, pbk, pred_table_dev, refs_dev) if pbk else \
+            eng.select_count(pspec, pred_table_dev, refs_dev)
     else:
         pcounts = torch.ones(E, dtype=torch.int64, device=dev)
     # ---- S2: observation selection ----
     ospec = make_sel_spec(sel_terms(local_select, list(table_cols), list(ref_cols)))
-    ocounts = eng.select_count(ospec, table_dev, refs_dev)
+    obk = eng.build_buckets(ospec, table_dev)
+    ocounts = eng.select_count_bucketed(ospec, obk, table_dev, refs_dev) if obk else \
+        eng.select_count(ospec, table_dev, refs_dev)
     has_pred = pcounts > 0                         # local_experts.py:962-965: skipped silently
     too_few = has_pred & (ocounts < min_obs)       # local_experts.py:988-1012: recorded, not run
     valid = has_pred & ~too_few
@@ -136,7 +140,9 @@ def run_experts(eng: Engine, spec: ModelSpec, table_dev: torch.Tensor, table_col
     poff[1:] = torch.cumsum(pcounts.index_select(0, vidx), 0)
     offs_host = torch.stack([ooff, poff]).cpu().numpy()      # one D2H sync for both CSR arrays
     ooff_h, poff_h = np.ascontiguousarray(offs_host[0]), np.ascontiguousarray(offs_host[1])
-    oidx = eng.select_fill(ospec, table_dev, refs_v, ooff, int(ooff_h[-1]))
+    omax = int(np.diff(ooff_h).max())
+    oidx = eng.select_fill_bucketed(ospec, obk, table_dev, refs_v, ooff, int(ooff_h[-1]), omax) \
+        if (obk and omax <= 32768) else eng.select_fill(ospec, table_dev, refs_v, ooff, int(ooff_h[-1]))
     coords, obs = eng.gather_rows(table_dev, oidx, [table_cols.index(c) for c in coords_col],
                                   table_cols.index(obs_col))
     cs = 1.0 if spec.coords_scale is None else spec.coords_scale
@@ -174,7 +180,9 @@ def run_experts(eng: Engine, spec: ModelSpec, table_dev: torch.Tensor, table_col
     # ---- F1 (+ L1: objective at the final parameters, local_experts.py:1135) ----
     if predict:
         if pred_table_dev is not None:
-            pidx = eng.select_fill(pspec, pred_table_dev, refs_v, poff, int(poff_h[-1]))
+            pmax = int(np.diff(poff_h).max())
+            pidx = eng.select_fill_bucketed(pspec, pbk, pred_table_dev, refs_v, poff, int(poff_h[-1]), pmax) \
+                if (pbk and pmax <= 32768) else eng.select_fill(pspec, pred_table_dev, refs_v, poff, int(poff_h[-1]))
             pcoords = eng.gather_pred(pred_table_dev, refs_v, poff, pidx,
                                       [pred_cols.index(c) if c in pred_cols else -1 for c in coords_col],
                                       [ref_cols.index(c) for c in coords_col])

@@ -662,6 +662,70 @@ extern "C" int gpsat_select_fill(const gpsat_sel_spec* spec, const double* table
   return select_common(spec, table_dev, n, refs_dev, nrefcols, E, 1, nullptr, offsets_dev, idx_dev, stream);
 }
 
+// ---- grid-bucketed selection ----
+static int find_ball_term(const gpsat_sel_spec* spec) {
+  for (int k = 0; k < spec->nterms; ++k)
+    if ((spec->t[k].type == 1 || spec->t[k].type == 2) && spec->t[k].ncol == 2) return k;
+  return -1;
+}
+static CellGrid make_grid(const gpsat_sel_spec* spec, int term, const gpsat_cell_grid* cg) {
+  CellGrid g;
+  g.x0 = cg->x0; g.y0 = cg->y0; g.inv_cell = 1.0 / cg->cell; g.ncx = cg->ncx; g.ncy = cg->ncy;
+  g.colx = spec->t[term].col[0]; g.coly = spec->t[term].col[1];
+  g.rcolx = spec->t[term].rcol[0]; g.rcoly = spec->t[term].rcol[1];
+  return g;
+}
+
+extern "C" int gpsat_bucket_build(const gpsat_sel_spec* spec, const gpsat_cell_grid* cg, const double* table_dev,
+                                  long long n, int pass, int* counts_dev, const long long* start_dev,
+                                  int* order_dev, void* stream) {
+  if (!spec || !cg || !table_dev || !counts_dev) return fail(GPSAT_EINVAL, "null argument");
+  const int term = find_ball_term(spec);
+  if (term < 0) return fail(GPSAT_EINVAL, "no two-column ball / max_dist term to bucket on");
+  if (!(cg->cell >= spec->t[term].val * 1.0000001)) return fail(GPSAT_EINVAL, "cell edge must exceed the radius");
+  if (n <= 0) return 0;
+  CellGrid g = make_grid(spec, term, cg);
+  const int grid = (int)std::min<long long>((n + 255) / 256, 148LL * 8);
+  if (pass == 0) {
+    k_cell_hist<<<grid, 256, 0, (cudaStream_t)stream>>>(g, table_dev, (long)n, counts_dev);
+  } else {
+    if (!start_dev || !order_dev) return fail(GPSAT_EINVAL, "null argument");
+    k_cell_scatter<<<grid, 256, 0, (cudaStream_t)stream>>>(g, table_dev, (long)n, start_dev, counts_dev, order_dev);
+  }
+  CK(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int gpsat_select_bucket(const gpsat_sel_spec* spec, const gpsat_cell_grid* cg, const double* table_dev,
+                                   long long n, const double* refs_dev, int nrefcols, int n_experts,
+                                   const long long* start_dev, const int* order_dev, int max_count,
+                                   long long* counts_dev, const long long* offsets_dev, int* idx_dev, void* stream) {
+  if (!spec || !cg || !table_dev || !refs_dev || !start_dev || !order_dev || nrefcols < 1 || nrefcols > 16)
+    return fail(GPSAT_EINVAL, "bad argument");
+  const int term = find_ball_term(spec);
+  if (term < 0) return fail(GPSAT_EINVAL, "no two-column ball / max_dist term to bucket on");
+  if (n_experts <= 0) return 0;
+  const int fill = counts_dev == nullptr;
+  if (fill && (!offsets_dev || !idx_dev)) return fail(GPSAT_EINVAL, "null output");
+  int cap = 1;
+  while (cap < std::max(max_count, 1)) cap <<= 1;
+  if (fill && cap > 32768) return fail(GPSAT_EINVAL, "more than 32768 matches per expert: use gpsat_select_fill");
+  SelSpec sp;
+  memcpy(&sp, spec, sizeof(sp));
+  CellGrid g = make_grid(spec, term, cg);
+  const size_t smem = fill ? (size_t)cap * sizeof(int) : 0;
+  static bool attr = false;
+  if (!attr) {
+    CK(cudaFuncSetAttribute(k_select_bucket, cudaFuncAttributeMaxDynamicSharedMemorySize, 32768 * sizeof(int)));
+    attr = true;
+  }
+  k_select_bucket<<<n_experts, 256, smem, (cudaStream_t)stream>>>(sp, g, table_dev, (long)n, refs_dev, nrefcols,
+                                                                  start_dev, order_dev, fill, cap, counts_dev,
+                                                                  offsets_dev, idx_dev);
+  CK(cudaGetLastError());
+  return 0;
+}
+
 extern "C" int gpsat_gather_rows(const double* table_dev, long long n, const int* idx_dev, long long total,
                                  int D, const int* coord_cols, int obs_col, double* coords_dev, double* obs_dev,
                                  void* stream) {

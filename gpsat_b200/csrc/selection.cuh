@@ -107,6 +107,94 @@ __global__ void __launch_bounds__(256) k_select(SelSpec sp, const double* __rest
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Grid-bucketed variant: rows are binned once into square cells of edge >= the query radius on the
+// two columns of the ball / max_dist term; an expert then tests only the rows of its 3 x 3 cell
+// neighbourhood with the SAME predicate arithmetic (bit-exact), collects the matches in shared memory
+// and sorts them, so the output is again in ascending source-row order.
+// ------------------------------------------------------------------------------------------------
+struct CellGrid {
+  double x0, y0, inv_cell;
+  int ncx, ncy, colx, coly, rcolx, rcoly;
+};
+__device__ __forceinline__ int cell_coord(double v, double v0, double inv_cell) {
+  const double f = floor((v - v0) * inv_cell);
+  return (int)fmax(-2.0, fmin(f, 2.0e9));
+}
+// counts[c] += 1 (hist) / order[start[c] + cursor[c]++] = row (scatter).  grid-stride over rows
+__global__ void __launch_bounds__(256) k_cell_hist(CellGrid g, const double* __restrict__ tab, long n, int* counts) {
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
+    const int cx = min(max(cell_coord(tab[(long)g.colx * n + i], g.x0, g.inv_cell), 0), g.ncx - 1);
+    const int cy = min(max(cell_coord(tab[(long)g.coly * n + i], g.y0, g.inv_cell), 0), g.ncy - 1);
+    atomicAdd(counts + (long)cy * g.ncx + cx, 1);
+  }
+}
+__global__ void __launch_bounds__(256) k_cell_scatter(CellGrid g, const double* __restrict__ tab, long n,
+                                                      const long long* __restrict__ start, int* cursor, int* order) {
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
+    const int cx = min(max(cell_coord(tab[(long)g.colx * n + i], g.x0, g.inv_cell), 0), g.ncx - 1);
+    const int cy = min(max(cell_coord(tab[(long)g.coly * n + i], g.y0, g.inv_cell), 0), g.ncy - 1);
+    const long c = (long)cy * g.ncx + cx;
+    order[start[c] + atomicAdd(cursor + c, 1)] = (int)i;
+  }
+}
+
+// grid (E), 256 threads, dynamic smem: cap ints (fill mode; cap = power of two >= max count)
+__global__ void __launch_bounds__(256) k_select_bucket(SelSpec sp, CellGrid g, const double* __restrict__ obs, long n,
+                                                       const double* __restrict__ refs, int nrefcols,
+                                                       const long long* __restrict__ start,
+                                                       const int* __restrict__ order, int fill, int cap,
+                                                       long long* counts, const long long* offsets, int* idx) {
+  extern __shared__ int list[];
+  __shared__ double ref[16];
+  __shared__ int nfound;
+  const int e = blockIdx.x;
+  if (threadIdx.x < nrefcols) ref[threadIdx.x] = refs[(long)e * nrefcols + threadIdx.x];
+  if (threadIdx.x == 0) nfound = 0;
+  __syncthreads();
+  const int ecx = cell_coord(ref[g.rcolx], g.x0, g.inv_cell), ecy = cell_coord(ref[g.rcoly], g.y0, g.inv_cell);
+  int local = 0;
+  for (int dy = -1; dy <= 1; ++dy) {
+    const int cy = ecy + dy;
+    if (cy < 0 || cy >= g.ncy) continue;
+    // rows clamped into the border cells may lie outside the nominal grid: widen the x-range there
+    const int cx0 = max(ecx - 1, 0), cx1 = min(ecx + 1, g.ncx - 1);
+    if (cx0 > cx1) continue;
+    const long long k0 = start[(long)cy * g.ncx + cx0], k1 = start[(long)cy * g.ncx + cx1 + 1];
+    for (long long k = k0 + threadIdx.x; k < k1; k += 256) {
+      const int row = order[k];
+      if (sel_match(sp, obs, n, row, ref)) {
+        if (fill) list[atomicAdd(&nfound, 1)] = row;
+        else ++local;
+      }
+    }
+  }
+  if (!fill) {
+    atomicAdd(&nfound, local);
+    __syncthreads();
+    if (threadIdx.x == 0) counts[e] = nfound;
+    return;
+  }
+  __syncthreads();
+  const int m = nfound;
+  for (int t = m + threadIdx.x; t < cap; t += 256) list[t] = 0x7fffffff;
+  __syncthreads();
+  for (int k2 = 2; k2 <= cap; k2 <<= 1)
+    for (int j = k2 >> 1; j > 0; j >>= 1) {
+      for (int t = threadIdx.x; t < cap; t += 256) {
+        const int p = t ^ j;
+        if (p > t) {
+          const int a = list[t], b = list[p];
+          const bool up = ((t & k2) == 0);
+          if ((a > b) == up) { list[t] = b; list[p] = a; }
+        }
+      }
+      __syncthreads();
+    }
+  const long long base = offsets[e];
+  for (int t = threadIdx.x; t < m; t += 256) idx[base + t] = list[t];
+}
+
 // gather selected rows of a column-major table into the CSR batch layout the GPR entry points
 // take: coords[total][D] row-major (from columns ccols[0..D-1]) and obs[total] (column ocol).
 struct GatherCols {

@@ -334,6 +334,53 @@ class Engine:
                                               nref, E, _ptr(offsets), _ptr(idx), _stream_ptr(self.device)))
         return idx[:total]
 
+    # ---- grid-bucketed S2 / S3 ----
+    def build_buckets(self, spec: "_lib.SelSpec", table_dev: torch.Tensor):
+        """Bin the table rows on the spec's two-column ball / max_dist term (None if it has none)."""
+        term = next((spec.t[k] for k in range(spec.nterms) if spec.t[k].type in (1, 2) and spec.t[k].ncol == 2), None)
+        n = table_dev.shape[1]
+        if term is None or n == 0 or not (term.val > 0):
+            return None
+        xs, ys = table_dev[term.col[0]], table_dev[term.col[1]]
+        lo = torch.stack([xs.min(), ys.min(), xs.max(), ys.max()]).cpu().numpy()
+        if not np.isfinite(lo).all():
+            return None
+        cell = float(term.val) * 1.000001
+        ncx = int((lo[2] - lo[0]) / cell) + 1
+        ncy = int((lo[3] - lo[1]) / cell) + 1
+        if ncx * ncy > (1 << 26):
+            return None
+        g = _lib.CellGrid(float(lo[0]), float(lo[1]), cell, ncx, ncy)
+        st = _stream_ptr(self.device)
+        counts = torch.zeros(ncx * ncy, dtype=torch.int32, device=self.device)
+        _lib.check(self.lib.gpsat_bucket_build(C.byref(spec), C.byref(g), _ptr(table_dev), n, 0, _ptr(counts), None,
+                                               None, st))
+        start = torch.zeros(ncx * ncy + 1, dtype=torch.int64, device=self.device)
+        start[1:] = torch.cumsum(counts, 0)
+        counts.zero_()
+        order = torch.empty(n, dtype=torch.int32, device=self.device)
+        _lib.check(self.lib.gpsat_bucket_build(C.byref(spec), C.byref(g), _ptr(table_dev), n, 1, _ptr(counts),
+                                               _ptr(start), _ptr(order), st))
+        return {"grid": g, "start": start, "order": order}
+
+    def select_count_bucketed(self, spec, buckets, table_dev, refs_dev):
+        E, nref = refs_dev.shape
+        counts = torch.zeros(E, dtype=torch.int64, device=self.device)
+        _lib.check(self.lib.gpsat_select_bucket(C.byref(spec), C.byref(buckets["grid"]), _ptr(table_dev),
+                                                table_dev.shape[1], _ptr(refs_dev), nref, E, _ptr(buckets["start"]),
+                                                _ptr(buckets["order"]), 0, _ptr(counts), None, None,
+                                                _stream_ptr(self.device)))
+        return counts
+
+    def select_fill_bucketed(self, spec, buckets, table_dev, refs_dev, offsets, total, max_count):
+        E, nref = refs_dev.shape
+        idx = torch.empty(max(total, 1), dtype=torch.int32, device=self.device)
+        _lib.check(self.lib.gpsat_select_bucket(C.byref(spec), C.byref(buckets["grid"]), _ptr(table_dev),
+                                                table_dev.shape[1], _ptr(refs_dev), nref, E, _ptr(buckets["start"]),
+                                                _ptr(buckets["order"]), int(max_count), None, _ptr(offsets),
+                                                _ptr(idx), _stream_ptr(self.device)))
+        return idx[:total]
+
     def select(self, spec: "_lib.SelSpec", table_dev: torch.Tensor, refs_dev: torch.Tensor):
         """Returns (offsets int64 [E+1], idx int32 [total]) on the device; indices ascending per expert."""
         counts = self.select_count(spec, table_dev, refs_dev)

@@ -108,6 +108,26 @@ int gpsat_select_fill(const gpsat_sel_spec* spec, const double* table_dev, long 
                       const double* refs_dev, int nrefcols, int n_experts,
                       const long long* offsets_dev, int* idx_dev, void* stream);
 
+/* Grid-bucketed S2 / S3 (same predicates, same bit-exact index sets, ascending row order): rows are
+ * binned once on the two columns of the spec's ball (type 1) or max_dist (type 2) term into square
+ * cells of edge `cell` > radius; an expert then only tests its 3 x 3 cell neighbourhood.
+ *   gpsat_bucket_build pass 0: counts_dev[ncx*ncy] += rows per cell (caller zeroes it, then exclusive-scans
+ *                              it into start_dev[ncx*ncy + 1] and zeroes counts_dev again)
+ *                      pass 1: order_dev[n] <- row ids grouped by cell (counts_dev is the cursor)
+ *   gpsat_select_bucket: counts_dev != NULL -> matches per expert; counts_dev == NULL -> fill idx_dev at
+ *                        offsets_dev (max_count = largest per-expert count, <= 32768). */
+typedef struct {
+  double x0, y0, cell;
+  int ncx, ncy;
+} gpsat_cell_grid;
+int gpsat_bucket_build(const gpsat_sel_spec* spec, const gpsat_cell_grid* grid, const double* table_dev,
+                       long long n, int pass, int* counts_dev, const long long* start_dev, int* order_dev,
+                       void* stream);
+int gpsat_select_bucket(const gpsat_sel_spec* spec, const gpsat_cell_grid* grid, const double* table_dev,
+                        long long n, const double* refs_dev, int nrefcols, int n_experts,
+                        const long long* start_dev, const int* order_dev, int max_count, long long* counts_dev,
+                        const long long* offsets_dev, int* idx_dev, void* stream);
+
 /* pack the selected rows into the CSR batch layout: coords_dev[total][D] <- table columns
  * coord_cols[0..D-1]; obs_dev[total] <- column obs_col (obs_col < 0: skipped).  Replaces
  * df.loc[select, :] + data[coords_col].values / data[obs_col].values

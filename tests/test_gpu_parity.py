@@ -327,3 +327,53 @@ def test_selection_large_random_vs_oracle(eng):
     for e in range(E):
         ref = selection.local_select_indices(cols, {"x": ex[e], "y": ey[e], "t": et[e]}, ls)
         np.testing.assert_array_equal(idx[off[e]:off[e + 1]], ref)
+
+
+def _bucketed(eng, spec, table, refs):
+    bk = eng.build_buckets(spec, table)
+    assert bk is not None
+    counts = eng.select_count_bucketed(spec, bk, table, refs)
+    off = torch.zeros(refs.shape[0] + 1, dtype=torch.int64, device=table.device)
+    off[1:] = torch.cumsum(counts, 0)
+    idx = eng.select_fill_bucketed(spec, bk, table, refs, off, int(off[-1]), int(counts.max()))
+    return off.cpu().numpy(), idx.cpu().numpy().astype(np.int64)
+
+
+def test_bucketed_selection_bit_exact(eng, golden_dir):
+    """grid-bucketed S2 / S3 against the reference's own index sets and against the brute-force kernel"""
+    from gpsat_b200.engine import make_sel_spec
+    g = _load(golden_dir, "select_3d.npz")
+    table = torch.as_tensor(np.stack([g["x"], g["y"], g["t"]])).cuda().contiguous()
+    refs = torch.as_tensor(np.column_stack([g["ex"], g["ey"], g["et"]])).cuda().contiguous()
+    spec = make_sel_spec([{"type": 0, "cols": [2], "rcols": [2], "comp": "<=", "val": float(g["t_hi"])},
+                          {"type": 0, "cols": [2], "rcols": [2], "comp": ">=", "val": float(g["t_lo"])},
+                          {"type": 1, "cols": [0, 1], "rcols": [0, 1], "val": float(g["radius"])}])
+    off, idx = _bucketed(eng, spec, table, refs)
+    np.testing.assert_array_equal(off, g["offsets"])
+    np.testing.assert_array_equal(idx, g["idx"])
+    g = _load(golden_dir, "predloc_2d.npz")
+    table = torch.as_tensor(np.stack([g["px"], g["py"]])).cuda().contiguous()
+    refs = torch.as_tensor(np.column_stack([g["ex"], g["ey"], g["et"]])).cuda().contiguous()
+    spec = make_sel_spec([{"type": 2, "cols": [0, 1], "rcols": [0, 1], "val": float(g["max_dist"])}])
+    off, idx = _bucketed(eng, spec, table, refs)
+    np.testing.assert_array_equal(off, g["offsets"])
+    np.testing.assert_array_equal(idx, g["idx"])
+    # lattice points exactly on the radius, experts outside the table's bounding box, empty results
+    rng = np.random.default_rng(5)
+    n, E = 300_000, 200
+    x = rng.integers(-60, 61, n) * 50_000.0
+    y = rng.integers(-60, 61, n) * 50_000.0
+    t = rng.integers(18316, 18337, n).astype(np.float64)
+    ex = rng.integers(-70, 71, E) * 50_000.0
+    ey = rng.integers(-70, 71, E) * 50_000.0
+    ex[:3], ey[:3] = [-9e6, 3.3e6, 0.0], [0.0, 3.3e6, 9e6]
+    table = torch.as_tensor(np.stack([x, y, t])).cuda().contiguous()
+    refs = torch.as_tensor(np.column_stack([ex, ey, np.full(E, 18326.0)])).cuda().contiguous()
+    spec = make_sel_spec([{"type": 0, "cols": [2], "rcols": [2], "comp": "<=", "val": 4.0},
+                          {"type": 0, "cols": [2], "rcols": [2], "comp": ">=", "val": -4.0},
+                          {"type": 1, "cols": [0, 1], "rcols": [0, 1], "val": 300_000.0}])
+    off, idx = _bucketed(eng, spec, table, refs)
+    off_b, idx_b = eng.select(spec, table, refs)
+    np.testing.assert_array_equal(off, off_b.cpu().numpy())
+    np.testing.assert_array_equal(idx, idx_b.cpu().numpy().astype(np.int64))
+    assert off[1] == 0 and off[-1] > 0
