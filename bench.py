@@ -35,7 +35,7 @@ def parse():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="c3", choices=["c3", "c1", "tiny"])
+    ap.add_argument("--workload", default="c3", choices=["c3", "c1", "c5", "tiny"])
     ap.add_argument("--experts-per-step", type=int, default=1024, help="experts per rank per step")
     ap.add_argument("--cpu-sample", type=int, default=1, help="experts timed by the cpu_baseline leg")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -103,9 +103,14 @@ def cpu_experts_per_sec(w, expert_rows, n_threads_note=True):
     ploc = pd.DataFrame({c: w["pred"][i] for i, c in enumerate(w["pred_cols"])})
     data = {"data_source": df, "obs_col": w["obs_col"], "coords_col": w["coords_col"],
             "local_select": w["local_select"]}
+    kw = {}
+    model = {k: v for k, v in w["model"].items() if k != "oi_model"}
+    if str(w["model"].get("oi_model", "")).endswith("SGPRModel"):
+        from oracle.sgpr import OracleSGPRModel
+        kw["model_cls"] = OracleSGPRModel
     t0 = time.perf_counter()
-    _, per = run_local_expert_oi(eloc, data, w["model"], {"method": "from_dataframe", "df": ploc,
-                                                          "max_dist": w["max_dist"]}, optimise=w["optimise"])
+    _, per = run_local_expert_oi(eloc, data, model, {"method": "from_dataframe", "df": ploc,
+                                                     "max_dist": w["max_dist"]}, optimise=w["optimise"], **kw)
     dt = time.perf_counter() - t0
     return len(per) / dt, dt, per
 

@@ -106,6 +106,21 @@ def workload(name="c3", n_experts=None, seed=SEED):
                     optimise=True,
                     describe="inline_example shape: 200 km expert lattice, ~400-600 obs per expert, "
                              "optimise + predict on the 5 km grid within 200 km")
+    if name == "c5":
+        # sparse path: GPflowSGPRModel-equivalent, 500 inducing points per expert, N ~ 2k-10k, 50 km expert lattice
+        E = 8192 if n_experts is None else n_experts
+        table = observations(rng, radius_cells=60, days=range(18316, 18337), density_lo=0.18, density_hi=0.85,
+                             n_sat=12)
+        experts = expert_lattice(E)
+        half = float(np.abs(experts[:, :2]).max()) + 30_000.0
+        model = dict(MODEL_C3, oi_model="B200SGPRModel",
+                     init_params=dict(MODEL_C3["init_params"], num_inducing_points=500))
+        return dict(name="c5", table=table, table_cols=["x", "y", "t", "obs"], experts=experts,
+                    expert_cols=["x", "y", "t"], pred=pred_grid(half), pred_cols=["x", "y"], max_dist=30_000.0,
+                    local_select=LOCAL_SELECT, model=model, coords_col=["x", "y", "t"], obs_col="obs",
+                    optimise=True,
+                    describe="sparse GPR, 500 inducing points per expert, 300 km radius / 9-day window, "
+                             "~2-10k obs per expert, L-BFGS optimise + predict on the 5 km grid within 30 km")
     if name == "tiny":
         E = 16 if n_experts is None else n_experts
         table = observations(rng, radius_cells=14, days=range(18322, 18331), density_lo=0.10, density_hi=0.16)
