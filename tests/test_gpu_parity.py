@@ -377,3 +377,59 @@ def test_bucketed_selection_bit_exact(eng, golden_dir):
     np.testing.assert_array_equal(off, off_b.cpu().numpy())
     np.testing.assert_array_equal(idx, idx_b.cpu().numpy().astype(np.int64))
     assert off[1] == 0 and off[-1] > 0
+
+
+# ---------------------------------------------------------------------------------------------
+# full-size experts (BASELINE configs 3 / 4: N ~ 2k and beyond) and failure handling
+# ---------------------------------------------------------------------------------------------
+def test_large_experts_objective_gradient_predict(eng):
+    rng = np.random.default_rng(41)
+    sizes = [2100, 4300]
+    Xs, zs = [], []
+    for n in sizes:
+        xy = rng.uniform(-3e5, 3e5, (n, 2))
+        t = rng.integers(18322, 18331, n).astype(np.float64)
+        X = np.column_stack([xy, t])
+        Xs.append(X)
+        zs.append(0.1 * np.sin(X[:, 0] / 2e5) + 0.05 * np.cos(X[:, 1] / 1.5e5) + rng.normal(0, 0.05, n))
+    cs = np.array([50_000.0, 50_000.0, 1.0])
+    off, Xc, zc = _pack(Xs, zs)
+    theta = np.array([[6.0, 5.0, 7.0, 0.012, 0.004], [4.0, 8.0, 5.0, 0.02, 0.003]])
+    b = eng.make_batch(off, Xc, zc, coords_scale=cs)
+    f, g = eng.eval(b, theta, grad=True)
+    f, g = f.cpu().numpy(), g.cpu().numpy()
+    P = 150
+    Xp = np.column_stack([rng.uniform(-2e5, 2e5, (P, 2)), np.full(P, 18326.0)])
+    fm, fv, _, _ = eng.predict(b, theta, np.array([0, P, 2 * P]), np.tile(Xp, (2, 1)))
+    fm, fv = fm.cpu().numpy(), fv.cpu().numpy()
+    for e in range(2):
+        fr, gr = gpr.neg_lml_and_grad(Xs[e] / cs, zs[e], theta[e, :3], theta[e, 3], theta[e, 4])
+        assert abs(f[e] - fr) <= RTOL_FIXED * abs(fr)
+        np.testing.assert_allclose(g[e], gr, rtol=1e-6, atol=1e-6 * np.abs(gr).max())
+        m, v, _ = gpr.predict(Xs[e] / cs, zs[e], Xp / cs, theta[e, :3], theta[e, 3], theta[e, 4])
+        np.testing.assert_allclose(fm[e * P:(e + 1) * P], m, rtol=1e-7, atol=1e-10)
+        np.testing.assert_allclose(fv[e * P:(e + 1) * P], v, rtol=1e-6, atol=1e-10)
+
+
+def test_non_positive_definite_is_reported_not_fatal(eng):
+    """The reference aborts the whole run on a failed Cholesky (uncaught TF exception); here the expert gets
+    f = +inf, the others are unaffected, and an optimisation started next to such a point still terminates."""
+    rng = np.random.default_rng(43)
+    X, z, cs = _synth(rng, 200)
+    Xd = np.vstack([X, X[:50]])                      # 50 exactly duplicated rows
+    zd = np.concatenate([z, z[:50] + 0.01])
+    off, Xc, zc = _pack([Xd, X], [zd, z])
+    b = eng.make_batch(off, Xc, zc, coords_scale=cs)
+    bad = np.array([5.0, 5.0, 5.0, 1.0, -1e-3])      # negative likelihood variance: K + nvar I is indefinite
+    good = np.array([5.0, 5.0, 5.0, 0.02, 0.004])
+    f, _ = eng.eval(b, np.stack([bad, good]), grad=True)
+    f = f.cpu().numpy()
+    assert np.isinf(f[0]) and f[0] > 0
+    fr = -gpr.lml(X / cs, z, good[:3], good[3], good[4])
+    assert abs(f[1] - fr) <= RTOL_FIXED * abs(fr)
+    f2, _ = eng.eval(b, np.stack([good, good]), grad=False)       # the failure flag does not stick
+    assert np.isfinite(f2.cpu().numpy()).all()
+    res = eng.optimise(b, np.array([1.0, 1.0, 1.0, 1.0, 1.0]), kind=[0] * 5, low=[0, 0, 0, 0, 1e-6], high=[0] * 5,
+                       trainable=[1] * 5, maxiter=60)
+    assert (res["status"].cpu().numpy() > 0).all()
+    assert np.isfinite(res["fobj"].cpu().numpy()).all()
