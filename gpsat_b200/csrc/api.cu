@@ -3,6 +3,7 @@
 
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <numeric>
 #include <string>
@@ -30,6 +31,9 @@ static int fail(int code, const std::string& msg) {
       return fail((int)e__, std::string(#call) + ": " + cudaGetErrorString(e__));         \
   } while (0)
 
+constexpr int MAX_GROUPS = 8;
+constexpr int MIN_GROUP_SLOTS = 32;
+
 struct Buf {
   void* p = nullptr;
   size_t cap = 0;
@@ -51,6 +55,12 @@ struct gpsat_handle {
   Buf Lt2, Xt2, Kt2, quad2, logdet2, fail2, sg_mm, sg_mn, sg_vec, sg_scal, sg_gpart, sg_ints, sg_beta, sg_ymean, sg_zeros;
   int* host_ints = nullptr;  // pinned
   size_t host_ints_cap = 0;
+  int max_slots = 0;         // 0: 4 slots per SM (GPSAT_MAX_SLOTS overrides)
+  int n_groups = 3;          // slot groups / streams of the optimiser (GPSAT_GROUPS overrides)
+  cudaStream_t gstream[8] = {};
+  cudaEvent_t gevent[8] = {};
+  cudaEvent_t ev_fork = nullptr;
+  int groups_ready = 0;
   bool attrs_set = false;
 };
 
@@ -100,6 +110,8 @@ extern "C" int gpsat_create(gpsat_handle** out, int device, size_t mem_budget_by
   gpsat_handle* h = new gpsat_handle();
   h->device = device;
   h->n_sm = prop.multiProcessorCount;
+  if (const char* eg = getenv("GPSAT_GROUPS")) h->n_groups = std::max(1, std::min(MAX_GROUPS, atoi(eg)));
+  if (const char* es = getenv("GPSAT_MAX_SLOTS")) h->max_slots = std::max(1, atoi(es));
   size_t free_b = 0, total_b = 0;
   CK(cudaMemGetInfo(&free_b, &total_b));
   h->budget = mem_budget_bytes ? mem_budget_bytes : (size_t)(0.7 * (double)free_b);
@@ -128,6 +140,8 @@ extern "C" int gpsat_destroy(gpsat_handle* h) {
   for (Buf* b : bs)
     if (b->p) cudaFree(b->p);
   if (h->host_ints) cudaFreeHost(h->host_ints);
+  for (int g = 0; g < h->groups_ready; ++g) { cudaStreamDestroy(h->gstream[g]); cudaEventDestroy(h->gevent[g]); }
+  if (h->ev_fork) cudaEventDestroy(h->ev_fork);
   for (auto e : h->ev) cudaEventDestroy(e);
   delete h;
   return 0;
@@ -181,7 +195,7 @@ static int make_plan(gpsat_handle* h, const gpsat_batch* b, Plan& pl, size_t ext
   const size_t per = slot_bytes(pl.nbmax) + extra_per_slot;
   long long cap = (long long)(h->budget / per);
   if (cap < 1) return fail(GPSAT_ENOMEM, "one expert of this size does not fit the memory budget");
-  pl.S = (int)std::min<long long>(std::min<long long>(E, cap), 4LL * h->n_sm);
+  pl.S = (int)std::min<long long>(std::min<long long>(E, cap), h->max_slots > 0 ? h->max_slots : 4LL * h->n_sm);
   return 0;
 }
 
@@ -189,6 +203,35 @@ struct Work {
   SlotCtx c;
   SlotAux a;
 };
+
+// the sub-pool [s0, s0 + Sg) of a slot pool
+static SlotCtx slot_view(const SlotCtx& c, int s0, int Sg) {
+  SlotCtx v = c;
+  v.S = Sg;
+  v.Lt += (size_t)s0 * c.tile_stride; v.Xt += (size_t)s0 * c.tile_stride; v.Kt += (size_t)s0 * c.tile_stride;
+  v.coords += (size_t)s0 * MAXD * c.npmax; v.yobs += (size_t)s0 * c.npmax;
+  v.n += s0; v.nb += s0; v.active += s0; v.fail += s0;
+  v.theta += (size_t)s0 * MAXP; v.logdet_part += (size_t)s0 * c.nbmax; v.quad += s0;
+  v.gpart += (size_t)s0 * c.ntmax * NG; v.fout += s0; v.gout += (size_t)s0 * MAXP;
+  return v;
+}
+
+static int ensure_groups(gpsat_handle* h, int G, int S) {
+  if (!h->ev_fork) CK(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
+  for (int g = h->groups_ready; g < G; ++g) {
+    CK(cudaStreamCreateWithFlags(&h->gstream[g], cudaStreamNonBlocking));
+    CK(cudaEventCreateWithFlags(&h->gevent[g], cudaEventDisableTiming));
+    h->groups_ready = g + 1;
+  }
+  const size_t need = (size_t)MAX_GROUPS * 3 * S + 8;
+  if (h->host_ints_cap < need) {
+    if (h->host_ints) cudaFreeHost(h->host_ints);
+    h->host_ints = nullptr;
+    CK(cudaMallocHost(&h->host_ints, need * sizeof(int)));
+    h->host_ints_cap = need;
+  }
+  return 0;
+}
 
 static int setup_work(gpsat_handle* h, const gpsat_batch* b, const Plan& pl, Work& w, cudaStream_t st) {
   const int S = pl.S;
@@ -410,27 +453,78 @@ extern "C" int gpsat_gpr_optimise(gpsat_handle* h, const gpsat_batch* b, const d
   k_slot_init<<<S, NTHREADS, 0, st>>>(w.c, w.a, bi, tr, 0, count, 1);
   ++h->launches;
   CK(cudaMemcpyAsync(w.a.queue_head, &count, sizeof(int), cudaMemcpyHostToDevice, st));
-  const long long max_rounds = (long long)(b->n_experts / S + 2) * (od.maxfun + od.maxls + 2);
-  for (long long round = 0; round < max_rounds; ++round) {
-    CK(cudaMemcpyAsync(h->host_ints, w.c.n, (size_t)3 * S * sizeof(int), cudaMemcpyDeviceToHost, st));
-    CK(cudaStreamSynchronize(st));
-    // layout of ints: n[S], nb[S], active[S]
-    int nact = 0, nbm = 0;
-    double fl = 0;
-    for (int s = 0; s < S; ++s) {
-      if (h->host_ints[2 * S + s]) {
-        ++nact;
-        nbm = std::max(nbm, h->host_ints[S + s]);
-        const double n = (double)h->host_ints[s];
-        fl += n * n * n / 3.0;
+  // The slot pool is split into independent groups, each advancing its own rounds on its own stream
+  // (all groups pull new experts from the one device work queue).  While one group sits in a serial or
+  // latency-bound stretch (diagonal-block factorisations, launch tails, the optimiser step, the host's
+  // look at the slot table) the other groups' CTAs fill the idle SMs.  Phase profiling keeps one group
+  // so that the event timings are not overlapped.
+  int G = (h->profiling || S < 2 * MIN_GROUP_SLOTS) ? 1 : std::min(h->n_groups, S / MIN_GROUP_SLOTS);
+  G = std::max(1, std::min(G, MAX_GROUPS));
+  r = ensure_groups(h, G, S);
+  if (r) return r;
+  struct Group { SlotCtx c; SlotAux a; int s0, Sg; bool done, pending; };
+  Group grp[MAX_GROUPS];
+  CK(cudaEventRecord(h->ev_fork, st));
+  for (int g = 0; g < G; ++g) {
+    Group& q = grp[g];
+    q.s0 = (int)((long long)S * g / G);
+    q.Sg = (int)((long long)S * (g + 1) / G) - q.s0;
+    q.c = slot_view(w.c, q.s0, q.Sg);
+    q.a = w.a;
+    q.a.slot_expert += q.s0;
+    q.a.states += q.s0;
+    q.done = false;
+    q.pending = false;
+    cudaStream_t sg = (G == 1) ? st : h->gstream[g];
+    if (G > 1) CK(cudaStreamWaitEvent(sg, h->ev_fork, 0));
+  }
+  const long long max_rounds = (long long)(b->n_experts / std::max(1, S / G) + 2) * (od.maxfun + od.maxls + 2);
+  int live = G;
+  for (long long round = 0; round < max_rounds && live > 0; ++round) {
+    for (int g = 0; g < G; ++g) {
+      Group& q = grp[g];
+      if (q.done) continue;
+      cudaStream_t sg = (G == 1) ? st : h->gstream[g];
+      int* hi = h->host_ints + (size_t)g * 3 * S;
+      if (!q.pending) {     // first look at this group's slot table
+        for (int k = 0; k < 3; ++k)
+          CK(cudaMemcpyAsync(hi + k * q.Sg, w.c.n + (size_t)k * S + q.s0, (size_t)q.Sg * sizeof(int),
+                             cudaMemcpyDeviceToHost, sg));
+        CK(cudaEventRecord(h->gevent[g], sg));
       }
+      CK(cudaEventSynchronize(h->gevent[g]));
+      int nact = 0, nbm = 0;
+      double fl = 0;
+      for (int k = 0; k < q.Sg; ++k) {
+        if (hi[2 * q.Sg + k]) {
+          ++nact;
+          nbm = std::max(nbm, hi[q.Sg + k]);
+          const double n = (double)hi[k];
+          fl += n * n * n / 3.0;
+        }
+      }
+      if (nact == 0) {
+        q.done = true;
+        --live;
+        continue;
+      }
+      r = run_round(h, q.c, nbm, true, true, sg, fl);
+      if (r) return r;
+      k_opt_step<<<q.Sg, NTHREADS, 0, sg>>>(q.c, q.a, bi, tr, lo, out);
+      ++h->launches;
+      for (int k = 0; k < 3; ++k)
+        CK(cudaMemcpyAsync(hi + k * q.Sg, w.c.n + (size_t)k * S + q.s0, (size_t)q.Sg * sizeof(int),
+                           cudaMemcpyDeviceToHost, sg));
+      CK(cudaEventRecord(h->gevent[g], sg));
+      q.pending = true;
+      if (h->profiling && h->ev_used > 4000) { CK(cudaStreamSynchronize(sg)); harvest_profile(h, true, true); }
     }
-    if (nact == 0) break;
-    r = run_round(h, w.c, nbm, true, true, st, fl);
-    if (r) return r;
-    k_opt_step<<<S, NTHREADS, 0, st>>>(w.c, w.a, bi, tr, lo, out);
-    ++h->launches;
-    if (h->profiling && h->ev_used > 4000) { CK(cudaStreamSynchronize(st)); harvest_profile(h, true, true); }
+  }
+  if (G > 1) {
+    for (int g = 0; g < G; ++g) {
+      CK(cudaEventRecord(h->gevent[g], h->gstream[g]));
+      CK(cudaStreamWaitEvent(st, h->gevent[g], 0));
+    }
   }
   CK(cudaStreamSynchronize(st));
   harvest_profile(h, true, true);

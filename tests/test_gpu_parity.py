@@ -433,3 +433,34 @@ def test_non_positive_definite_is_reported_not_fatal(eng):
                        trainable=[1] * 5, maxiter=60)
     assert (res["status"].cpu().numpy() > 0).all()
     assert np.isfinite(res["fobj"].cpu().numpy()).all()
+
+
+def test_slot_groups_on_streams_are_bitwise_equivalent(eng):
+    """>= 64 resident experts: the optimiser splits the slot pool into groups on separate streams; results must
+    be identical to a single-group run (each expert's arithmetic does not depend on the grouping)."""
+    from gpsat_b200.engine import Engine
+    rng = np.random.default_rng(77)
+    sizes = list(rng.integers(20, 90, 100))
+    Xs, zs = [], []
+    for n in sizes:
+        X, z, cs = _synth(rng, int(n))
+        Xs.append(X)
+        zs.append(z)
+    off, Xc, zc = _pack(Xs, zs)
+    m0 = _oracle_model(Xs[0], zs[0], cs)
+    theta0 = np.concatenate([m0.get_lengthscales(), [m0.get_kernel_variance()], [m0.get_likelihood_variance()]])
+    kind, low, high = m0._transforms_flat()
+    res = {}
+    for g in ("1", "3"):
+        os.environ["GPSAT_GROUPS"] = g
+        e2 = Engine(0)
+        try:
+            b = e2.make_batch(off, Xc, zc, coords_scale=cs, obs_mean_local=True)
+            r = e2.optimise(b, theta0, kind, low, high, trainable=[1] * 5)
+            res[g] = {k: r[k].cpu().numpy() for k in ("theta", "fobj", "status", "nit", "nfev")}
+        finally:
+            e2.close()
+            os.environ.pop("GPSAT_GROUPS", None)
+    for k in res["1"]:
+        np.testing.assert_array_equal(res["1"][k], res["3"][k], err_msg=k)
+    assert (res["3"]["status"] > 0).all()
