@@ -78,6 +78,23 @@ def h_of_r2(r2, variance, kernel):
     return np.where(r2 > 1e-36, variance * np.exp(-r) / r, 0.0)
 
 
+def kh_of_r2(r2, variance, kernel):
+    """(k, h) sharing the exponential (same values as k_of_r2 / h_of_r2)."""
+    kid = KERNEL_IDS[kernel]
+    if kid == 3:
+        k = variance * np.exp(-0.5 * r2)
+        return k, k.copy()
+    r = np.sqrt(np.maximum(r2, 1e-36))
+    if kid == 0:
+        e = np.exp(-SQRT3 * r)
+        return variance * (1.0 + SQRT3 * r) * e, 3.0 * variance * e
+    if kid == 1:
+        e = np.exp(-SQRT5 * r)
+        return variance * (1.0 + SQRT5 * r + 5.0 / 3.0 * (r * r)) * e, variance * (5.0 / 3.0) * (1.0 + SQRT5 * r) * e
+    k = variance * np.exp(-r)
+    return k, np.where(r2 > 1e-36, k / r, 0.0)
+
+
 def kernel_matrix(X, X2, ls, variance, kernel="Matern32", form="direct"):
     return k_of_r2(scaled_sqdist(X, X2, ls, form), variance, kernel)
 
@@ -96,26 +113,40 @@ def lml(X, y, ls, kvar, nvar, kernel="Matern32", form="direct"):
 
 
 def neg_lml_and_grad(X, y, ls, kvar, nvar, kernel="Matern32"):
-    """(-LML, d(-LML)/d[ls..., kvar, nvar]) using the direct distance form."""
+    """(-LML, d(-LML)/d[ls..., kvar, nvar]) using the direct distance form.
+
+    LAPACK potrf / potri (threaded) so that the CPU baseline timed by bench.py is not handicapped by
+    an explicit triangular inverse; raises LinAlgError when K is not positive definite.
+    """
     n, D = X.shape
-    r2 = scaled_sqdist(X, None, ls, "direct")
-    Kf = k_of_r2(r2, kvar, kernel)
+    Xs = X / ls
+    d2 = []
+    r2 = np.zeros((n, n))
+    for d in range(D):                      # fixed summation order d = 0, 1, 2 (matches scaled_sqdist / the device)
+        dd = Xs[:, None, d] - Xs[None, :, d]
+        dd *= dd
+        d2.append(dd)
+        r2 += dd
+    Kf, h = kh_of_r2(r2, kvar, kernel)
     K = Kf.copy()
     K[np.diag_indices(n)] += nvar
-    L = np.linalg.cholesky(K)
-    Linv = sla.solve_triangular(L, np.eye(n), lower=True)
-    Kinv = Linv.T @ Linv
-    a = Linv @ y
-    alpha = Linv.T @ a
+    L, info = sla.lapack.dpotrf(K, lower=1, clean=1, overwrite_a=1)
+    if info != 0:
+        raise np.linalg.LinAlgError("matrix is not positive definite")
+    a = sla.solve_triangular(L, y, lower=True)
+    alpha = sla.solve_triangular(L, a, lower=True, trans="T")
+    Kinv, info = sla.lapack.dpotri(L, lower=1, overwrite_c=0)
+    if info != 0:
+        raise np.linalg.LinAlgError("dpotri failed")
+    Kinv = np.tril(Kinv) + np.tril(Kinv, -1).T
     f = 0.5 * float(a @ a) + float(np.sum(np.log(np.diag(L)))) + 0.5 * n * LOG2PI
-    W = Kinv - np.outer(alpha, alpha)
-    h = h_of_r2(r2, kvar, kernel)
+    W = Kinv
+    W -= np.outer(alpha, alpha)
     g = np.zeros(D + 2)
-    WH = W * h
+    h *= W
     for d in range(D):
-        delta = X[:, None, d] - X[None, :, d]
-        g[d] = 0.5 * np.sum(WH * delta * delta) / ls[d] ** 3
-    g[D] = 0.5 * np.sum(W * Kf) / kvar
+        g[d] = 0.5 * float(np.einsum("ij,ij->", h, d2[d])) / ls[d]
+    g[D] = 0.5 * float(np.einsum("ij,ij->", W, Kf)) / kvar
     g[D + 1] = 0.5 * np.trace(W)
     return f, g
 
