@@ -99,6 +99,11 @@ _EXPORTS = {
     "gpsat_launch_count": (C.c_longlong, [C.c_void_p]),
     "gpsat_set_profiling": (C.c_int, [C.c_void_p, C.c_int]),
     "gpsat_get_profile": (C.c_int, [C.c_void_p] + [C.POINTER(C.c_double)] * 7),
+    "gpsat_gaussian_smooth": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_longlong, C.c_void_p, C.c_void_p,
+                                        C.c_void_p, C.c_void_p, C.c_double, C.c_double, C.POINTER(C.c_double),
+                                        C.POINTER(C.c_double), C.c_void_p, C.c_void_p]),
+    "gpsat_weighted_groups": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_longlong, C.c_int,
+                                        C.c_void_p, C.c_void_p, C.c_longlong, C.c_double, C.c_void_p, C.c_void_p]),
     "gpsat_dmma_peak": (C.c_int, [C.c_int, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
     "gpsat_microbench": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_double)]),
     "gpsat_lbfgs_state_bytes": (C.c_size_t, []),

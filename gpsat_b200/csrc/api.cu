@@ -13,6 +13,7 @@
 #include "selection.cuh"
 #include "microbench.cuh"
 #include "sgpr.cuh"
+#include "postproc.cuh"
 
 using namespace gpsat;
 
@@ -974,6 +975,37 @@ extern "C" int gpsat_microbench(int device, int which, int param, int nk, double
   }
   cudaFree(buf);
   return r;
+}
+
+// ---- post-processing ----
+extern "C" int gpsat_gaussian_smooth(const double* qx_dev, const double* qy_dev, const int* seg_of_query_dev,
+                                     long long n_query, const double* x_dev, const double* y_dev,
+                                     const double* vals_dev, const long long* seg_off_dev, double l_x, double l_y,
+                                     const double* vmin, const double* vmax, double* out_dev, void* stream) {
+  if (!qx_dev || !qy_dev || !seg_of_query_dev || !x_dev || !y_dev || !vals_dev || !seg_off_dev || !out_dev ||
+      !(l_x > 0) || !(l_y > 0))
+    return fail(GPSAT_EINVAL, "bad argument");
+  if (n_query <= 0) return 0;
+  k_gauss_smooth<<<(unsigned)n_query, 256, 0, (cudaStream_t)stream>>>(
+      qx_dev, qy_dev, seg_of_query_dev, x_dev, y_dev, vals_dev, seg_off_dev, l_x, l_y, vmin ? *vmin : 0.0,
+      vmax ? *vmax : 0.0, vmin != nullptr, vmax != nullptr, out_dev);
+  CK(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int gpsat_weighted_groups(const double* ref_dev, const double* to_dev, int nd, const double* vals_dev,
+                                     long long n, int ncol, const long long* order_dev,
+                                     const long long* group_off_dev, long long n_groups, double lengthscale,
+                                     double* out_dev, void* stream) {
+  if (!ref_dev || !to_dev || nd < 1 || (ncol > 0 && !vals_dev) || ncol < 0 || !order_dev || !group_off_dev ||
+      !out_dev || !(lengthscale > 0))
+    return fail(GPSAT_EINVAL, "bad argument");
+  if (n_groups <= 0) return 0;
+  k_weighted_groups<<<(unsigned)n_groups, 256, 0, (cudaStream_t)stream>>>(
+      ref_dev, to_dev, nd, vals_dev, (long)n, ncol, order_dev, group_off_dev, lengthscale * lengthscale,
+      (long)n_groups, out_dev);
+  CK(cudaGetLastError());
+  return 0;
 }
 
 // ---- host-side L-BFGS hooks (same code the device runs) ----

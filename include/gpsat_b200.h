@@ -213,6 +213,24 @@ int gpsat_set_profiling(gpsat_handle* h, int enabled);
 int gpsat_get_profile(gpsat_handle* h, double* ms_potrf, double* ms_trtri, double* ms_lauum,
                       double* ms_other, double* flops_potrf, double* flops_trtri, double* flops_lauum);
 
+/* Post-processing either side of the hot path.
+ * gpsat_gaussian_smooth replaces gaussian_2d_weight (GPSat/postprocessing.py:22-52) as called by
+ *   smooth_hyperparameters (postprocessing.py:269-292): out[i] = sum_j w_ij v_j / sum_j w_ij over the rows j of the
+ *   segment of query i, w_ij = exp(-(((x_j - qx_i)/l_x)^2 + ((y_j - qy_i)/l_y)^2) / 2); NaN values are skipped, a
+ *   segment with no finite value yields NaN; vmin / vmax (host pointers, NULL = none) clip the values first.
+ *   Rows are grouped by segment: seg_off[G+1] (int64), seg_of_query[n_query] (int32).
+ * gpsat_weighted_groups replaces get_weighted_values (GPSat/utils.py:2081-2214) and the Gaussian glue
+ *   (postprocessing.py:447-577): ref / to are [nd][n] column-major, vals [ncol][n]; group g = source rows
+ *   order[group_off[g] .. group_off[g+1]); w = exp(-(|ref - to|^2 / lengthscale^2) / 2);
+ *   out [ncol + 1][G] = weighted mean per column, last row = sum of w. */
+int gpsat_gaussian_smooth(const double* qx_dev, const double* qy_dev, const int* seg_of_query_dev,
+                          long long n_query, const double* x_dev, const double* y_dev, const double* vals_dev,
+                          const long long* seg_off_dev, double l_x, double l_y, const double* vmin,
+                          const double* vmax, double* out_dev, void* stream);
+int gpsat_weighted_groups(const double* ref_dev, const double* to_dev, int nd, const double* vals_dev, long long n,
+                          int ncol, const long long* order_dev, const long long* group_off_dev,
+                          long long n_groups, double lengthscale, double* out_dev, void* stream);
+
 /* roofline denominator for the factorisation kernels: FP64 mma.sync (DMMA m8n8k4) issue rate of
  * this GPU measured with register-resident accumulator chains (no memory traffic). */
 int gpsat_dmma_peak(int device, int iters, double* tflops_out, double* ms_out);

@@ -21,4 +21,7 @@ Pinning status (see DESIGN.md "Oracle"):
     scipy.optimize.minimize itself (same f/g callable).  GPflow's own rounding
     (matmul-form r^2) cannot be executed here: "gpflow form" is restated, not
     pinned, and differs from the direct form at the 1e-7..1e-9 level.
+  * post-processing (oracle/postproc.py): pinned against the
+    reference's own gaussian_2d_weight, get_weighted_values and
+    glue_local_predictions_1d/_2d outputs (tests/golden/postproc.npz).
 """
