@@ -2,6 +2,7 @@
 #include "../../include/gpsat_b200.h"
 
 #include <algorithm>
+#include <chrono>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -481,6 +482,12 @@ extern "C" int gpsat_gpr_optimise(gpsat_handle* h, const gpsat_batch* b, const d
   }
   const long long max_rounds = (long long)(b->n_experts / std::max(1, S / G) + 2) * (od.maxfun + od.maxls + 2);
   int live = G;
+  // GPSAT_TRACE=<file>: per group and round, host time at which the previous round of the group was seen
+  // complete + the active-slot census (diagnostic: slot-pool utilisation over a batch)
+  FILE* trace = nullptr;
+  if (const char* tp = getenv("GPSAT_TRACE")) trace = fopen(tp, "a");
+  const auto t_trace0 = std::chrono::steady_clock::now();
+  if (trace) fprintf(trace, "# optimise E=%d S=%d G=%d\n", b->n_experts, S, G);
   for (long long round = 0; round < max_rounds && live > 0; ++round) {
     for (int g = 0; g < G; ++g) {
       Group& q = grp[g];
@@ -504,6 +511,10 @@ extern "C" int gpsat_gpr_optimise(gpsat_handle* h, const gpsat_batch* b, const d
           fl += n * n * n / 3.0;
         }
       }
+      if (trace)
+        fprintf(trace, "%lld,%d,%.1f,%d,%d,%.4g\n", round, g,
+                std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - t_trace0).count(), nact,
+                nbm, fl);
       if (nact == 0) {
         q.done = true;
         --live;
@@ -528,6 +539,7 @@ extern "C" int gpsat_gpr_optimise(gpsat_handle* h, const gpsat_batch* b, const d
     }
   }
   CK(cudaStreamSynchronize(st));
+  if (trace) fclose(trace);
   harvest_profile(h, true, true);
   CK(cudaGetLastError());
   return 0;

@@ -4,14 +4,19 @@
 // ------------------------------------------------------
 // A symmetric / triangular N x N matrix of one expert is stored as PACKED LOWER-TRIANGULAR
 // 64 x 64 TILES: tile (i, j), j <= i, lives at tile index i*(i+1)/2 + j and is one contiguous
-// 32 KiB blob, so a whole operand tile is one linear bulk copy into shared memory.
-// Inside a tile element (r, c) is stored at   r*64 + (c ^ ((r & 3) << 2))   (doubles).
-// That XOR swizzle makes BOTH DMMA fragment access patterns bank-conflict free straight
-// from the copied image (no padding, no re-layout pass):
-//   row pattern  : lane reads (row0 + lane/4, k0 + lane%4)
-//   col pattern  : lane reads (k0 + lane%4, col0 + lane/4)
-// (a 64-bit shared load is served per half-warp over 16 8-byte banks; in both patterns the
-//  16 lanes of a half-warp hit 16 distinct banks.)
+// 32 KiB blob made of two 64 x 32 COLUMN HALVES (16 KiB each, columns 0-31 then 32-63).
+// Inside a tile element (r, c) is stored at
+//       (c >> 5) * 2048 + r * 32 + ((c & 31) ^ ((r & 3) << 2))        (doubles).
+// Consequences:
+//   * a 32-deep k-slice of an operand is contiguous in global memory whichever way k runs: along the
+//     columns it is one column half (one 16 KiB TMA bulk copy), along the rows it is rows
+//     [32h, 32h+32) of both halves (two 8 KiB bulk copies) -- no per-thread cp.async traffic at all;
+//   * the XOR swizzle makes BOTH DMMA fragment access patterns bank-conflict free straight from
+//     the copied image (no padding, no re-layout pass):
+//       row pattern  : lane reads (row0 + lane/4, k0 + lane%4)
+//       col pattern  : lane reads (k0 + lane%4, col0 + lane/4)
+//     (a 64-bit shared load is served per half-warp over 16 8-byte banks; in both patterns the
+//      16 lanes of a half-warp hit 16 distinct banks.)
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -27,7 +32,10 @@ constexpr int NTHREADS = 256;          // CTA size of the tile kernels (8 warps:
 
 enum KernelId { K_MATERN32 = 0, K_MATERN52 = 1, K_MATERN12 = 2, K_RBF = 3 };
 
-__host__ __device__ __forceinline__ int swz(int r, int c) { return r * TB + (c ^ ((r & 3) << 2)); }
+constexpr int HALF_ELEMS = TB * 32;    // one 64 x 32 column half = 2048 doubles = 16 KiB
+__host__ __device__ __forceinline__ int swz(int r, int c) {
+  return ((c >> 5) << 11) + r * 32 + ((c & 31) ^ ((r & 3) << 2));
+}
 __host__ __device__ __forceinline__ long tri_index(int i, int j) { return (long)i * (i + 1) / 2 + j; }
 
 // ---- cp.async (LDGSTS) 16-byte copies ----
@@ -47,6 +55,40 @@ __device__ __forceinline__ void load_tile_async(double* smem_tile, const double*
     cp_async16(reinterpret_cast<char*>(smem_tile) + idx * 16,
                reinterpret_cast<const char*>(gmem_tile) + idx * 16);
   }
+}
+
+// ---- mbarrier + TMA bulk copy (cp.async.bulk, SASS UBLKCP; completion counted on an mbarrier) ----
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void fence_mbar_init() {
+  asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred P1;\n"
+      "LAB_WAIT:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+      "@P1 bra DONE;\n"
+      "bra LAB_WAIT;\n"
+      "DONE:\n"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+// one thread: copy `bytes` (multiple of 16, both addresses 16-byte aligned) global -> shared
+__device__ __forceinline__ void bulk_g2s(void* smem, const void* gmem, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(
+                   smem_u32(smem)),
+               "l"(gmem), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
 }
 
 // ---- FP64 tensor-core MMA: D(8x8) += A(8x4) * B(4x8) ----

@@ -2,24 +2,27 @@
 //
 // One CTA (8 warps, 2 along M x 4 along N, 64x32 per warp) owns a 2x2 group of 64x64 output
 // tiles and streams operand tiles (packed swizzled 32 KiB blobs, see common.cuh) through a
-// 3-stage cp.async ring of 32-deep k-slices:  per slice 4 half-tiles (2 of A, 2 of B) = 64 KiB,
+// 3-stage ring of 32-deep k-slices:  per slice 4 half-tiles (2 of A, 2 of B) = 64 KiB,
 // 128x128x32 FMAs -> 32 KiB of operand traffic per 64^3 tile product (half of the 64x64 core).
+// The ring is filled by TMA bulk copies (cp.async.bulk -> SASS UBLKCP) issued by ONE thread and
+// tracked by one mbarrier per stage (expect_tx / complete_tx); the 256 compute threads issue no
+// copy instructions at all.  (The previous per-thread cp.async version lost 14 % of the DMMA rate:
+// 4096 LDGSTS per slice queue in front of the fragment LDS in the same MIO pipe.)
 // Fragments are double-buffered in registers so the shared-memory loads of step k+4 are in
 // flight while the 32 DMMAs of step k issue.
 //
 // Operand orientation (per tile, straight from the swizzled image):
 //   TA  = false: A[m][k] = Atile(m, k)  (k along tile columns)   TA  = true: A[m][k] = Atile(k, m)
 //   TBm = false: B[k][n] = Btile(n, k)                            TBm = true: B[k][n] = Btile(k, n)
-// A k-slice of a "k along columns" tile is the 64 x 32 column half (row stride 32 in shared
-// memory, the XOR swizzle only touches column bits 2-3 so it survives the split); a k-slice of a
-// "k along rows" tile is 32 full rows (contiguous 16 KiB).
+// A k-slice of a "k along columns" tile is one 64 x 32 column half (contiguous 16 KiB, row stride 32);
+// a k-slice of a "k along rows" tile is rows [32h, 32h+32) of both column halves (two contiguous
+// 8 KiB pieces, kept side by side in shared memory: [half][32 rows][32 cols]).
 #pragma once
 #include "common.cuh"
 
 namespace gpsat {
 
 constexpr int G2_STAGES = 3;
-constexpr int HALF_ELEMS = TB * 32;                  // 2048 doubles = 16 KiB
 constexpr int G2_STAGE_ELEMS = 4 * HALF_ELEMS;       // A0 A1 B0 B1
 constexpr int G2_SMEM_ELEMS = G2_STAGES * G2_STAGE_ELEMS;   // 24576 doubles = 192 KiB
 
@@ -50,20 +53,14 @@ struct Frag2 {
   __device__ __forceinline__ int col(int ni) const { return nb0 + 8 * ni + 2 * r; }   // within tile tb (and col+1)
 };
 
-// issue the cp.async copies of one half-tile (16 KiB) with all NTHREADS threads
-template <bool KROWS>   // KROWS: k runs along tile rows (contiguous slice); else along columns
-__device__ __forceinline__ void load_half_async(double* smem_half, const double* gmem_tile, int kh) {
-  const char* src = reinterpret_cast<const char*>(gmem_tile);
-  char* dst = reinterpret_cast<char*>(smem_half);
-#pragma unroll
-  for (int c = 0; c < 4; ++c) {
-    const int idx = threadIdx.x + c * NTHREADS;   // 0..1023 chunks of 16 B
-    if (KROWS) {
-      cp_async16(dst + idx * 16, src + kh * 16384 + idx * 16);
-    } else {
-      const int rr = idx >> 4, x = idx & 15;
-      cp_async16(dst + rr * 256 + x * 16, src + rr * 512 + kh * 256 + x * 16);
-    }
+// one thread: bulk-copy one 32-deep k-slice (16 KiB) of a tile into a shared-memory half
+template <bool KROWS>   // KROWS: k runs along tile rows; else along columns
+__device__ __forceinline__ void bulk_half(double* smem_half, const double* gmem_tile, int kh, uint64_t* bar) {
+  if (KROWS) {
+    bulk_g2s(smem_half, gmem_tile + kh * 1024, 8192, bar);
+    bulk_g2s(smem_half + 1024, gmem_tile + HALF_ELEMS + kh * 1024, 8192, bar);
+  } else {
+    bulk_g2s(smem_half, gmem_tile + kh * HALF_ELEMS, 16384, bar);
   }
 }
 
@@ -76,12 +73,12 @@ __device__ __forceinline__ void mma_half(Acc2& acc, const double* __restrict__ A
 #pragma unroll
   for (int mi = 0; mi < 8; ++mi) {
     const int m = 8 * mi + f.q;
-    aoff[mi] = TA ? (f.r * TB + (m ^ (f.r << 2))) : (m * 32 + f.r);
+    aoff[mi] = TA ? ((m >> 5) * 1024 + f.r * 32 + ((m & 31) ^ (f.r << 2))) : (m * 32 + f.r);
   }
 #pragma unroll
   for (int ni = 0; ni < 4; ++ni) {
     const int n = f.nb0 + 8 * ni + f.q;
-    boff[ni] = TBm ? (f.r * TB + (n ^ (f.r << 2))) : (n * 32 + f.r);
+    boff[ni] = TBm ? ((n >> 5) * 1024 + f.r * 32 + ((n & 31) ^ (f.r << 2))) : (n * 32 + f.r);
   }
   double a[2][8], b[2][4];
 #pragma unroll
@@ -94,9 +91,9 @@ __device__ __forceinline__ void mma_half(Acc2& acc, const double* __restrict__ A
     if (ks + 1 < 8) {
       const int kk = (ks + 1) * 4;
 #pragma unroll
-      for (int mi = 0; mi < 8; ++mi) a[nxt][mi] = As[aoff[mi] + (TA ? kk * TB : (kk ^ sq))];
+      for (int mi = 0; mi < 8; ++mi) a[nxt][mi] = As[aoff[mi] + (TA ? kk * 32 : (kk ^ sq))];
 #pragma unroll
-      for (int ni = 0; ni < 4; ++ni) b[nxt][ni] = Bs[boff[ni] + (TBm ? kk * TB : (kk ^ sq))];
+      for (int ni = 0; ni < 4; ++ni) b[nxt][ni] = Bs[boff[ni] + (TBm ? kk * 32 : (kk ^ sq))];
     }
 #pragma unroll
     for (int mi = 0; mi < 8; ++mi)
@@ -105,43 +102,98 @@ __device__ __forceinline__ void mma_half(Acc2& acc, const double* __restrict__ A
   }
 }
 
+// Ring state of one CTA: mbarriers in shared memory + the number of slices that went through the ring so far
+// (stage and phase parity of slice n are n % G2_STAGES and (n / G2_STAGES) & 1), so several pipelines can run
+// back to back in one kernel.  init() must be called by all threads once, before the first pipeline.
+struct G2Pipe {
+  uint64_t* full;
+  uint32_t count;
+  __device__ __forceinline__ void init() {
+    __shared__ __align__(8) uint64_t bars[G2_STAGES];
+    full = bars;
+    count = 0;
+    if (threadIdx.x == 0) {
+#pragma unroll
+      for (int s = 0; s < G2_STAGES; ++s) mbar_init(bars + s, 1);
+      fence_mbar_init();
+    }
+    __syncthreads();
+  }
+  __device__ __forceinline__ int stage(uint32_t n) const { return (int)(n % G2_STAGES); }
+  __device__ __forceinline__ void wait(uint32_t n) const { mbar_wait(full + stage(n), (n / G2_STAGES) & 1u); }
+};
+
+struct NoTail {
+  __device__ __forceinline__ const double* operator()(int, int) const { return nullptr; }
+};
+
 // acc += sum_{k = kbeg}^{kend-1} [A_k^0; A_k^1] * [B_k^0  B_k^1]  over 64-deep tile steps.
 // a_of(k, t) / b_of(k, t), t in {0,1}: global pointer of the tile or nullptr (structurally zero /
 // out of range: the copy and the products that would use it are skipped; nullness must be
-// CTA-uniform).  smem: G2_SMEM_ELEMS doubles.  Ends with all copies drained and a __syncthreads().
-template <bool TA, bool TBm, class FA, class FB>
-__device__ __forceinline__ void gemm2_pipeline(Acc2& acc, double* smem, int kbeg, int kend, FA a_of, FB b_of,
-                                               const Frag2& f) {
-  const int nsl = 2 * (kend - kbeg);   // 32-deep slices
-  if (nsl <= 0) return;
-  auto issue = [&](int sl) {
-    const int k = kbeg + (sl >> 1), kh = sl & 1;
-    double* st = smem + (sl % G2_STAGES) * G2_STAGE_ELEMS;
-#pragma unroll
-    for (int t = 0; t < 2; ++t) {
-      const double* pa = a_of(k, t);
-      if (pa) load_half_async<TA>(st + t * HALF_ELEMS, pa, kh);
-      const double* pb = b_of(k, t);
-      if (pb) load_half_async<TBm>(st + (2 + t) * HALF_ELEMS, pb, kh);
+// CTA-uniform).  smem: G2_SMEM_ELEMS doubles.
+// TAIL: after the last k-slice two more ring slots are filled with whole tiles tail_of(e, t), e, t in {0,1}
+// (e.g. the C tiles an epilogue needs), fetched while the last slices are being multiplied; slot e lands in
+// tail[e] (tile t at tail[e] + t * TILE_ELEMS, missing tiles are not touched).  Without TAIL the call ends with
+// every copy consumed and a __syncthreads(); with TAIL the caller reads the tiles and then must __syncthreads()
+// before the ring is reused.
+template <bool TA, bool TBm, bool TAIL, class FA, class FB, class FT>
+__device__ __forceinline__ void gemm2_pipeline_t(Acc2& acc, double* smem, G2Pipe& p, int kbeg, int kend, FA a_of,
+                                                 FB b_of, const Frag2& f, FT tail_of, const double** tail) {
+  const int nsl = (kend > kbeg) ? 2 * (kend - kbeg) : 0;   // 32-deep slices
+  const int ntot = nsl + (TAIL ? 2 : 0);
+  if (ntot == 0) return;
+  auto issue = [&](int sl) {    // thread 0 only
+    const uint32_t n = p.count + sl;
+    double* st = smem + p.stage(n) * G2_STAGE_ELEMS;
+    uint64_t* bar = p.full + p.stage(n);
+    if (sl < nsl) {
+      const int k = kbeg + (sl >> 1), kh = sl & 1;
+      const double* pa0 = a_of(k, 0);
+      const double* pa1 = a_of(k, 1);
+      const double* pb0 = b_of(k, 0);
+      const double* pb1 = b_of(k, 1);
+      mbar_expect_tx(bar, 16384u * ((pa0 != nullptr) + (pa1 != nullptr) + (pb0 != nullptr) + (pb1 != nullptr)));
+      if (pa0) bulk_half<TA>(st, pa0, kh, bar);
+      if (pa1) bulk_half<TA>(st + HALF_ELEMS, pa1, kh, bar);
+      if (pb0) bulk_half<TBm>(st + 2 * HALF_ELEMS, pb0, kh, bar);
+      if (pb1) bulk_half<TBm>(st + 3 * HALF_ELEMS, pb1, kh, bar);
+    } else {
+      const int e = sl - nsl;
+      const double* t0 = tail_of(e, 0);
+      const double* t1 = tail_of(e, 1);
+      mbar_expect_tx(bar, 32768u * ((t0 != nullptr) + (t1 != nullptr)));
+      if (t0) bulk_g2s(st, t0, 32768, bar);
+      if (t1) bulk_g2s(st + TILE_ELEMS, t1, 32768, bar);
     }
   };
-  issue(0);
-  cp_async_commit();
-  if (nsl > 1) issue(1);
-  cp_async_commit();
+  if (threadIdx.x == 0) {
+    for (int sl = 0; sl < G2_STAGES && sl < ntot; ++sl) issue(sl);
+  }
   for (int sl = 0; sl < nsl; ++sl) {
-    cp_async_wait<1>();      // slice sl has landed (one younger group may be in flight)
-    __syncthreads();         // ... for every thread; and everyone is done with slice sl-1's buffer
-    if (sl + 2 < nsl) issue(sl + 2);
-    cp_async_commit();
+    const uint32_t n = p.count + sl;
+    p.wait(n);               // the slice has landed
     const int k = kbeg + (sl >> 1);
     if (a_of(k, f.ta) != nullptr && b_of(k, f.tb) != nullptr) {
-      const double* st = smem + (sl % G2_STAGES) * G2_STAGE_ELEMS;
+      const double* st = smem + p.stage(n) * G2_STAGE_ELEMS;
       mma_half<TA, TBm>(acc, st + f.ta * HALF_ELEMS, st + (2 + f.tb) * HALF_ELEMS, f);
     }
+    __syncthreads();         // everyone is done with this ring slot
+    if (threadIdx.x == 0 && sl + G2_STAGES < ntot) issue(sl + G2_STAGES);
   }
-  cp_async_wait<0>();
-  __syncthreads();
+  if (TAIL) {
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {
+      p.wait(p.count + nsl + e);
+      tail[e] = smem + p.stage(p.count + nsl + e) * G2_STAGE_ELEMS;
+    }
+  }
+  p.count += ntot;
+}
+
+template <bool TA, bool TBm, class FA, class FB>
+__device__ __forceinline__ void gemm2_pipeline(Acc2& acc, double* smem, G2Pipe& p, int kbeg, int kend, FA a_of,
+                                               FB b_of, const Frag2& f) {
+  gemm2_pipeline_t<TA, TBm, false>(acc, smem, p, kbeg, kend, a_of, b_of, f, NoTail(), nullptr);
 }
 
 // store this warp's 64x32 slab into a swizzled 64x64 tile (global or shared), scaled

@@ -40,26 +40,28 @@ struct FragCoord {
 template <bool TA, bool TBm>
 __device__ __forceinline__ void mma_tile(Acc& acc, const double* __restrict__ As,
                                          const double* __restrict__ Bs, const FragCoord& fc) {
+  // tile image (common.cuh): (r, c) at (c >> 5) * 2048 + r * 32 + ((c & 31) ^ ((r & 3) << 2))
   int abase[2], bbase[4];
   const int sq = (fc.q & 3) << 2;
 #pragma unroll
   for (int mi = 0; mi < 2; ++mi) {
     const int m = 16 * fc.wm + 8 * mi + fc.q;
-    abase[mi] = TA ? (fc.r * TB + (m ^ (fc.r << 2))) : (m * TB + fc.r);
+    abase[mi] = TA ? ((m >> 5) * HALF_ELEMS + fc.r * 32 + ((m & 31) ^ (fc.r << 2))) : (m * 32 + fc.r);
   }
 #pragma unroll
   for (int ni = 0; ni < 4; ++ni) {
     const int n = 32 * fc.wn + 8 * ni + fc.q;
-    bbase[ni] = TBm ? (fc.r * TB + (n ^ (fc.r << 2))) : (n * TB + fc.r);
+    bbase[ni] = TBm ? ((n >> 5) * HALF_ELEMS + fc.r * 32 + ((n & 31) ^ (fc.r << 2))) : (n * 32 + fc.r);
   }
 #pragma unroll
   for (int k0 = 0; k0 < TB; k0 += 4) {
     double a[2], b[4];
-    const int kx = k0 ^ sq;  // row pattern: (k0 + r) ^ sq == (k0 ^ sq) + r
+    // k along columns: half k0 >> 5, column (k0 & 31) + r, swizzled by the row: ((k0 & 31) ^ sq) + r
+    const int kx = (k0 >> 5) * HALF_ELEMS + ((k0 & 31) ^ sq);
 #pragma unroll
-    for (int mi = 0; mi < 2; ++mi) a[mi] = TA ? As[abase[mi] + k0 * TB] : As[abase[mi] + kx];
+    for (int mi = 0; mi < 2; ++mi) a[mi] = TA ? As[abase[mi] + k0 * 32] : As[abase[mi] + kx];
 #pragma unroll
-    for (int ni = 0; ni < 4; ++ni) b[ni] = TBm ? Bs[bbase[ni] + k0 * TB] : Bs[bbase[ni] + kx];
+    for (int ni = 0; ni < 4; ++ni) b[ni] = TBm ? Bs[bbase[ni] + k0 * 32] : Bs[bbase[ni] + kx];
 #pragma unroll
     for (int mi = 0; mi < 2; ++mi)
 #pragma unroll

@@ -211,16 +211,26 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_potrf_update2(SlotCtx c, int J)
   double* Lt = c.Lt + (long)s * c.tile_stride;
   double* Kt = c.Kt + (long)s * c.tile_stride;
   Frag2 f;
+  G2Pipe pipe;
+  pipe.init();
   Acc2 acc;
   acc.zero();
-  gemm2_pipeline<false, false>(
-      acc, smem, 0, j0,
-      [&](int k, int t) -> const double* { return (2 * I + t < nb) ? tile_ptr(Lt, 2 * I + t, k) : nullptr; },
-      [&](int k, int t) -> const double* { return (j0 + t < nb) ? tile_ptr(Lt, j0 + t, k) : nullptr; }, f);
   const int ti = 2 * I + f.ta, tj = j0 + f.tb;
   const bool valid = (ti < nb) && (tj < nb) && (tj <= ti);
+  // the four K_aug tiles of this group ride through the ring behind the last k-slices (tail), so the
+  // epilogue reads them from shared memory instead of waiting on 32 dependent global loads per thread
+  const double* ktile[2];
+  gemm2_pipeline_t<false, false, true>(
+      acc, smem, pipe, 0, j0,
+      [&](int k, int t) -> const double* { return (2 * I + t < nb) ? tile_ptr(Lt, 2 * I + t, k) : nullptr; },
+      [&](int k, int t) -> const double* { return (j0 + t < nb) ? tile_ptr(Lt, j0 + t, k) : nullptr; }, f,
+      [&](int e, int t) -> const double* {
+        const int a = 2 * I + e, b = j0 + t;
+        return (a < nb && b < nb && b <= a) ? tile_ptr(Kt, a, b) : nullptr;
+      },
+      ktile);
   if (valid) {
-    const double* kt = tile_ptr(Kt, ti, tj);
+    const double* kt = ktile[f.ta] + f.tb * TILE_ELEMS;
 #pragma unroll
     for (int mi = 0; mi < 8; ++mi)
 #pragma unroll
@@ -244,7 +254,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_potrf_update2(SlotCtx c, int J)
   double* P3 = P2 + TILE_ELEMS;     // L10
   double* dg = smem + (SMEM2_ELEMS - G2_AUX);
   const bool two = (j1 < nb);
-  // the pipeline ended with a barrier: shared memory is free
+  __syncthreads();   // every warp has read its K tile: the ring is free
   if (f.ta == 0 && f.tb == 0) {
 #pragma unroll
     for (int mi = 0; mi < 8; ++mi)
@@ -317,11 +327,13 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_potrf_trsm2(SlotCtx c, int J) {
   double* Lt = c.Lt + (long)s * c.tile_stride;
   double* Xt = c.Xt + (long)s * c.tile_stride;
   Frag2 f;
+  G2Pipe pipe;
+  pipe.init();
   Acc2 acc;
   acc.zero();
   const int kend = (j0 + 1 < nb) ? 2 : 1;
   gemm2_pipeline<false, false>(
-      acc, smem, 0, kend,
+      acc, smem, pipe, 0, kend,
       [&](int k, int t) -> const double* { return (2 * I + t < nb) ? tile_ptr(Lt, 2 * I + t, j0 + k) : nullptr; },
       [&](int k, int t) -> const double* {
         return (t >= k && j0 + t < nb) ? tile_ptr(Xt, j0 + t, j0 + k) : nullptr;
@@ -373,10 +385,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_trtri_pass1(SlotCtx c, int h) {
   double* Lt = c.Lt + (long)s * c.tile_stride;
   double* Xt = c.Xt + (long)s * c.tile_stride;
   Frag2 f;
+  G2Pipe pipe;
+  pipe.init();
   Acc2 acc;
   acc.zero();
   gemm2_pipeline<false, true>(
-      acc, smem, 2 * Q, 2 * mid,
+      acc, smem, pipe, 2 * Q, 2 * mid,
       [&](int k, int t) -> const double* { return (2 * P + t < nb) ? tile_ptr(Lt, 2 * P + t, k) : nullptr; },
       [&](int k, int t) -> const double* { return (k >= 2 * Q + t) ? x_tile(c, s, k, 2 * Q + t) : nullptr; }, f);
   const int ti = 2 * P + f.ta, tj = 2 * Q + f.tb;
@@ -393,11 +407,13 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_trtri_pass2(SlotCtx c, int h) {
   double* Lt = c.Lt + (long)s * c.tile_stride;
   double* Xt = c.Xt + (long)s * c.tile_stride;
   Frag2 f;
+  G2Pipe pipe;
+  pipe.init();
   Acc2 acc;
   acc.zero();
   const int kend = (2 * P + 2 < nb) ? 2 * P + 2 : nb;
   gemm2_pipeline<false, true>(
-      acc, smem, 2 * mid, kend,
+      acc, smem, pipe, 2 * mid, kend,
       [&](int k, int t) -> const double* {
         return (2 * P + t < nb && k <= 2 * P + t) ? x_tile(c, s, 2 * P + t, k) : nullptr;
       },
@@ -417,10 +433,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_lauum2(SlotCtx c) {
   if (I >= nsr) return;
   double* Kt = c.Kt + (long)s * c.tile_stride;
   Frag2 f;
+  G2Pipe pipe;
+  pipe.init();
   Acc2 acc;
   acc.zero();
   gemm2_pipeline<true, true>(
-      acc, smem, 2 * I, nb,
+      acc, smem, pipe, 2 * I, nb,
       [&](int k, int t) -> const double* {
         return (2 * I + t < nb && k >= 2 * I + t) ? x_tile(c, s, k, 2 * I + t) : nullptr;
       },
@@ -615,6 +633,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_predict2(SlotCtx c, PredCtx p) 
   const double* scr = p.scratch + (long)blockIdx.x * c.nbmax * 2 * TILE_ELEMS;
   const double kvar = c.theta[s * MAXP + c.D];
   Frag2 f;
+  G2Pipe pipe;
+  pipe.init();
   double csq[4][2];
 #pragma unroll
   for (int ni = 0; ni < 4; ++ni) csq[ni][0] = csq[ni][1] = 0.0;
@@ -624,7 +644,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_predict2(SlotCtx c, PredCtx p) 
     acc.zero();
     const int kend = (2 * I + 2 < nb) ? 2 * I + 2 : nb;
     gemm2_pipeline<false, true>(
-        acc, smem, 0, kend,
+        acc, smem, pipe, 0, kend,
         [&](int k, int t) -> const double* {
           return (2 * I + t < nb && k <= 2 * I + t) ? x_tile(c, s, 2 * I + t, k) : nullptr;
         },
@@ -697,11 +717,13 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_pred_cov(SlotCtx c, PredCtx p, 
   tri_decode(blockIdx.x, bp, bq);
   const int s = 0, nb = c.nb[s], P = p.np[s];
   Frag2 f;
+  G2Pipe pipe;
+  pipe.init();
   Acc2 acc;
   acc.zero();
   const long istride = (long)c.nbmax * 2 * TILE_ELEMS;
   gemm2_pipeline<true, true>(
-      acc, smem, 0, nb,
+      acc, smem, pipe, 0, nb,
       [&](int k, int t) -> const double* { return p.abuf + bp * istride + ((long)k * 2 + t) * TILE_ELEMS; },
       [&](int k, int t) -> const double* { return p.abuf + bq * istride + ((long)k * 2 + t) * TILE_ELEMS; }, f);
   const double* th = c.theta + s * MAXP;

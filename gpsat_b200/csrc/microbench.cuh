@@ -75,6 +75,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_gemm2_bench(const double* tiles
                                                              double* out) {
   extern __shared__ __align__(128) double smem[];
   Frag2 f;
+  G2Pipe pipe;
+  pipe.init();
   Acc2 acc;
   acc.zero();
   if (mode == 0) {
@@ -84,7 +86,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_gemm2_bench(const double* tiles
   } else {
     const double* base = tiles + (mode == 1 ? (long)blockIdx.x * tiles_per_cta * TILE_ELEMS : 0L);
     gemm2_pipeline<TA, TBm>(
-        acc, smem, 0, nk,
+        acc, smem, pipe, 0, nk,
         [&](int k, int t) { return base + ((long)(4 * k + t) % tiles_per_cta) * TILE_ELEMS; },
         [&](int k, int t) { return base + ((long)(4 * k + 2 + t) % tiles_per_cta) * TILE_ELEMS; }, f);
   }

@@ -169,10 +169,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_tgemm(TGemm p, int njs) {
   if (p.kmode == 2) kbeg = 2 * I;
   if (p.kmode == 3) kbeg = 2 * J;
   Frag2 f;
+  G2Pipe pipe;
+  pipe.init();
   Acc2 acc;
   acc.zero();
   gemm2_pipeline<TA, TBm>(
-      acc, smem, kbeg, kend,
+      acc, smem, pipe, kbeg, kend,
       [&](int k, int t) -> const double* {
         const int i = 2 * I + t;
         if (i >= mt) return nullptr;
