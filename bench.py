@@ -25,6 +25,10 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
+# per-launch DRAM traffic (bytes) of the dominant kernel of each phase, from the committed ncu --set full captures
+# (profiles/*_summary.md); filled in when a capture of the current kernel generation exists
+TRAFFIC = {}
+
 METRIC = "experts/sec (optimise+predict)"
 UNIT = "experts/s"
 
@@ -296,18 +300,24 @@ def run_b200(args):
             dist.destroy_process_group()
         return
 
-    # ---- roofline of the dominant kernel group: the batched Cholesky (k_potrf_update + k_potrf_trsm) ----
+    # ---- roofline of the dominant kernel group: the batched Cholesky (k_potrf_panel launches of every round) ----
     phases = {}
     for nm in ("potrf", "trtri", "lauum"):
         t_ms, fl = prof[f"ms_{nm}"], prof[f"flops_{nm}"]
         phases[nm] = {"ms": t_ms, "tflops": (fl / (t_ms * 1e-3) / 1e12) if t_ms > 0 else None}
-    dom = max(phases, key=lambda k: phases[k]["ms"])
+    for nm in ("build", "trace", "other"):      # FP64-pipe elementwise kernels (no N^3 work): time only
+        phases[nm] = {"ms": prof[f"ms_{nm}"], "tflops": None}
+    dom = max(("potrf", "trtri", "lauum"), key=lambda k: phases[k]["ms"])
     peak = max(dmma_peak, dgemm_peak)
-    roofline = {"bound": "tensor", "kernel": {"potrf": "k_potrf_update+k_potrf_trsm (batched Cholesky)",
-                                              "trtri": "k_trtri_step (triangular inverse)",
-                                              "lauum": "k_lauum_trace (K^-1 tiles + gradient trace)"}[dom],
+    roofline = {"bound": "tensor", "kernel": {"potrf": "k_potrf_panel (batched blocked Cholesky, one launch per panel)",
+                                              "trtri": "k_trtri_pass1/2 (triangular inverse)",
+                                              "lauum": "k_lauum2 (K^-1 tiles)"}[dom],
                 "achieved": phases[dom]["tflops"], "peak": peak, "unit": "TFLOP/s",
-                "frac": (phases[dom]["tflops"] / peak) if phases[dom]["tflops"] else None, "traffic": None,
+                "frac": (phases[dom]["tflops"] / peak) if phases[dom]["tflops"] else None,
+                "traffic": TRAFFIC.get(dom),
+                "traffic_note": "dram__bytes_read.sum + dram__bytes_write.sum per launch of the phase's dominant kernel, "
+                                "from the committed ncu --set full capture (profiles/); null when not captured for "
+                                "this kernel generation",
                 "peak_source": f"FP64 measured on this GPU in this run: DMMA register-chain {dmma_peak:.1f} TF, "
                                f"cuBLAS DGEMM 4096^3 {dgemm_peak:.1f} TF (MEASURED_PEAKS.json has no FP64 entry)",
                 "flops_model": "sum over active experts of N^3/3 per phase per objective evaluation",

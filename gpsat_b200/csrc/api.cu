@@ -47,7 +47,7 @@ struct gpsat_handle {
   int n_sm = 148;
   long long launches = 0;
   bool profiling = false;
-  double ms[4] = {0, 0, 0, 0};
+  double ms[6] = {0, 0, 0, 0, 0, 0};   // potrf, trtri, lauum, other (finalize), build, trace
   double fl[3] = {0, 0, 0};
   std::vector<cudaEvent_t> ev;
   size_t ev_used = 0;
@@ -59,6 +59,7 @@ struct gpsat_handle {
   size_t host_ints_cap = 0;
   int max_slots = 0;         // 0: 4 slots per SM (GPSAT_MAX_SLOTS overrides)
   int n_groups = 3;          // slot groups / streams of the optimiser (GPSAT_GROUPS overrides)
+  int fused_panels = 1;      // Cholesky panels as one fused launch each (GPSAT_UNFUSED_POTRF=1: update + trsm launches)
   cudaStream_t gstream[8] = {};
   cudaEvent_t gevent[8] = {};
   cudaEvent_t ev_fork = nullptr;
@@ -117,6 +118,8 @@ extern "C" int gpsat_create(gpsat_handle** out, int device, size_t mem_budget_by
   size_t free_b = 0, total_b = 0;
   CK(cudaMemGetInfo(&free_b, &total_b));
   h->budget = mem_budget_bytes ? mem_budget_bytes : (size_t)(0.7 * (double)free_b);
+  if (const char* eu = getenv("GPSAT_UNFUSED_POTRF")) h->fused_panels = atoi(eu) ? 0 : 1;
+  CK(cudaFuncSetAttribute(k_potrf_panel, cudaFuncAttributeMaxDynamicSharedMemorySize, PANEL_SMEM_BYTES));
   CK(cudaFuncSetAttribute(k_potrf_update2, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM2_BYTES));
   CK(cudaFuncSetAttribute(k_potrf_trsm2, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM2_BYTES));
   CK(cudaFuncSetAttribute(k_trtri_pass1, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM2_BYTES));
@@ -153,15 +156,17 @@ extern "C" long long gpsat_launch_count(const gpsat_handle* h) { return h ? h->l
 extern "C" int gpsat_set_profiling(gpsat_handle* h, int enabled) {
   if (!h) return GPSAT_EINVAL;
   h->profiling = enabled != 0;
-  for (int k = 0; k < 4; ++k) h->ms[k] = 0;
+  for (int k = 0; k < 6; ++k) h->ms[k] = 0;
   for (int k = 0; k < 3; ++k) h->fl[k] = 0;
   return 0;
 }
 extern "C" int gpsat_get_profile(gpsat_handle* h, double* a, double* b, double* c, double* d, double* fa,
-                                 double* fb, double* fc) {
+                                 double* fb, double* fc, double* ms_build, double* ms_trace) {
   if (!h) return GPSAT_EINVAL;
   *a = h->ms[0]; *b = h->ms[1]; *c = h->ms[2]; *d = h->ms[3];
   *fa = h->fl[0]; *fb = h->fl[1]; *fc = h->fl[2];
+  if (ms_build) *ms_build = h->ms[4];
+  if (ms_trace) *ms_trace = h->ms[5];
   return 0;
 }
 
@@ -212,7 +217,7 @@ static SlotCtx slot_view(const SlotCtx& c, int s0, int Sg) {
   v.S = Sg;
   v.Lt += (size_t)s0 * c.tile_stride; v.Xt += (size_t)s0 * c.tile_stride; v.Kt += (size_t)s0 * c.tile_stride;
   v.coords += (size_t)s0 * MAXD * c.npmax; v.yobs += (size_t)s0 * c.npmax;
-  v.n += s0; v.nb += s0; v.active += s0; v.fail += s0;
+  v.n += s0; v.nb += s0; v.active += s0; v.fail += s0; v.pflag += s0;
   v.theta += (size_t)s0 * MAXP; v.logdet_part += (size_t)s0 * c.nbmax; v.quad += s0;
   v.gpart += (size_t)s0 * c.ntmax * NG; v.fout += s0; v.gout += (size_t)s0 * MAXP;
   return v;
@@ -243,7 +248,7 @@ static int setup_work(gpsat_handle* h, const gpsat_batch* b, const Plan& pl, Wor
   ENS(h->quad, (size_t)S * 8);
   ENS(h->coords, (size_t)S * MAXD * pl.npmax * 8);
   ENS(h->yobs, (size_t)S * pl.npmax * 8);
-  ENS(h->ints, (size_t)(6 * S + 8) * sizeof(int));
+  ENS(h->ints, (size_t)(7 * S + 8) * sizeof(int));
   ENS(h->theta, (size_t)S * MAXP * 8);
   ENS(h->logdet, (size_t)S * pl.nbmax * 8);
   ENS(h->gpart, (size_t)S * pl.ntmax * NG * 8);
@@ -263,13 +268,13 @@ static int setup_work(gpsat_handle* h, const gpsat_batch* b, const Plan& pl, Wor
   c.tile_stride = (long)pl.ntmax * TILE_ELEMS;
   c.Lt = (double*)h->Lt.p; c.Xt = (double*)h->Xt.p; c.Kt = (double*)h->Kt.p; c.quad = (double*)h->quad.p;
   c.coords = (double*)h->coords.p; c.yobs = (double*)h->yobs.p;
-  c.n = ip; c.nb = ip + S; c.active = ip + 2 * S; c.fail = ip + 3 * S;
+  c.n = ip; c.nb = ip + S; c.active = ip + 2 * S; c.fail = ip + 3 * S; c.pflag = ip + 6 * S;
   c.theta = (double*)h->theta.p; c.logdet_part = (double*)h->logdet.p; c.gpart = (double*)h->gpart.p;
   c.fout = (double*)h->fout.p; c.gout = (double*)h->gout.p;
   w.a.slot_expert = ip + 4 * S;
   w.a.queue_head = ip + 5 * S;
   w.a.states = (LbfgsState*)h->states.p;
-  CK(cudaMemsetAsync(h->ints.p, 0, (size_t)(6 * S + 8) * sizeof(int), st));
+  CK(cudaMemsetAsync(h->ints.p, 0, (size_t)(7 * S + 8) * sizeof(int), st));
   CK(cudaMemcpyAsync(h->order.p, pl.order.data(), (size_t)b->n_experts * sizeof(int), cudaMemcpyHostToDevice, st));
   return 0;
 }
@@ -306,7 +311,13 @@ static int run_round_flags(gpsat_handle* h, const SlotCtx& c, int nbm, int flags
     k_build<<<dim3(ntm, c.S), 256, 0, st>>>(c);
     ++h->launches;
   }
+  if (prof) cudaEventRecord(next_event(h), st);
   for (int J = 0; J < nsr; ++J) {
+    if (h->fused_panels) {
+      k_potrf_panel<<<c.S + c.S * (nsr - J - 1), NTHREADS, PANEL_SMEM_BYTES, st>>>(c, J, nsr);
+      ++h->launches;
+      continue;
+    }
     k_potrf_update2<<<dim3(nsr - J, c.S), NTHREADS, SMEM2_BYTES, st>>>(c, J);
     ++h->launches;
     if (J + 1 < nsr) {
@@ -330,6 +341,7 @@ static int run_round_flags(gpsat_handle* h, const SlotCtx& c, int nbm, int flags
     k_lauum2<<<dim3(nsr * (nsr + 1) / 2, c.S), NTHREADS, SMEM2_BYTES, st>>>(c);
     ++h->launches;
   }
+  if (prof) cudaEventRecord(next_event(h), st);
   if (flags & RR_TRACE) {
     k_grad_trace<<<dim3(ntm, c.S), 256, 0, st>>>(c);
     ++h->launches;
@@ -351,11 +363,11 @@ static int run_round(gpsat_handle* h, const SlotCtx& c, int nbm, bool inverse, b
 
 static void harvest_profile(gpsat_handle* h, bool inverse, bool grad) {
   if (!h->profiling) { h->ev_used = 0; h->ev_flops.clear(); return; }
-  const size_t rounds = h->ev_used / 5;
+  const size_t rounds = h->ev_used / 7;
   for (size_t r = 0; r < rounds; ++r) {
-    float t[4];
-    for (int k = 0; k < 4; ++k) cudaEventElapsedTime(&t[k], h->ev[5 * r + k], h->ev[5 * r + k + 1]);
-    h->ms[0] += t[0]; h->ms[1] += t[1]; h->ms[2] += t[2]; h->ms[3] += t[3];
+    float t[6];   // build | potrf + quad | trtri | lauum | trace | finalize
+    for (int k = 0; k < 6; ++k) cudaEventElapsedTime(&t[k], h->ev[7 * r + k], h->ev[7 * r + k + 1]);
+    h->ms[4] += t[0]; h->ms[0] += t[1]; h->ms[1] += t[2]; h->ms[2] += t[3]; h->ms[5] += t[4]; h->ms[3] += t[5];
     h->fl[0] += h->ev_flops[r];
     if (inverse) h->fl[1] += h->ev_flops[r];
     if (grad) h->fl[2] += h->ev_flops[r];

@@ -37,17 +37,19 @@ struct Acc2 {
 };
 
 struct Frag2 {
-  int lane, warp, q, r, wm, wn, ta, tb, nb0;
+  int lane, warp, q, r, ta, tb, nb0;
   __device__ __forceinline__ Frag2() {
     lane = threadIdx.x & 31;
     warp = threadIdx.x >> 5;
     q = lane >> 2;
     r = lane & 3;
-    wm = warp & 1;        // which A tile (row tile of the 2x2 group)
-    wn = warp >> 1;       // 0..3: 32-column slab
-    ta = wm;
-    tb = wn >> 1;         // which B tile (column tile of the 2x2 group)
-    nb0 = (wn & 1) * 32;  // column offset inside that tile
+    // Warp w runs on scheduler w % 4 (the DMMA pipe is per scheduler).  The two warps of a scheduler own
+    // diagonally opposite tiles of the 2x2 group, (ta, tb) and (1 - ta, 1 - tb): whenever one A tile or one B
+    // tile of a k-step is structurally zero, every scheduler keeps exactly one busy warp, so the skipped
+    // products shorten the step instead of idling half of the pipes.
+    ta = warp >> 2;                   // which A tile (row tile of the 2x2 group)
+    tb = ((warp >> 1) & 1) ^ ta;      // which B tile (column tile of the 2x2 group)
+    nb0 = (warp & 1) * 32;            // 32-column slab inside that tile
   }
   __device__ __forceinline__ int row(int mi) const { return 8 * mi + q; }             // within tile ta
   __device__ __forceinline__ int col(int ni) const { return nb0 + 8 * ni + 2 * r; }   // within tile tb (and col+1)

@@ -50,6 +50,7 @@ struct SlotCtx {
   double* quad;             // [S] a'a
   double* gpart;            // [S][ntmax][NG]
   int* fail;                // [S] set when a pivot is not positive
+  int* pflag;               // [S] k_potrf_panel: J + 1 once the diagonal block of panel J is published (k_quad resets)
   double* fout;             // [S]  -LML
   double* gout;             // [S][MAXP] d(-LML)/dtheta (constrained parameters)
 };
@@ -343,6 +344,209 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_potrf_trsm2(SlotCtx c, int J) {
   if (ti < nb && tj < nb) store_acc2(tile_ptr(Lt, ti, tj), acc, f);
 }
 
+// ------------------------------------------------------------------------------------
+// Fused potrf panel J (replaces k_potrf_update2 + k_potrf_trsm2: one launch per panel, the C block never
+// goes through global memory).  1-D grid, diagonal CTAs first:
+//   blocks [0, S)            : slot b, supertile row I = J: update + 128x128 factorisation (as k_potrf_update2),
+//                              then publish pflag[s] = J + 1 (release)
+//   blocks [S, S + S * nd)   : nd = nsr_max - J - 1; slot (b - S) / nd, row I = J + 1 + (b - S) % nd:
+//                              C = K - sum_k L_Ik L_Jk' in registers -> shared memory (4 tile images), wait for the
+//                              slot's flag (blocks are dispatched in index order, so its diagonal CTA started at
+//                              least a wave earlier), fetch X_JJ = L_JJ^-1 (3 tiles) by TMA and form
+//                              L_I,panel = C X_JJ' from shared memory.
+// Shared memory: ring [0, 192 KiB) (later C [0, 128) + X10, X11 [128, 192)) + X00 [192, 224 KiB).
+// ------------------------------------------------------------------------------------
+constexpr int PANEL_SMEM_ELEMS = G2_SMEM_ELEMS + TILE_ELEMS + 64;   // + X00 + dg of the diagonal CTA
+constexpr int PANEL_SMEM_BYTES = PANEL_SMEM_ELEMS * 8;
+static_assert(DIAG_ELEMS + 64 <= PANEL_SMEM_ELEMS, "diagonal workspace must fit");
+static_assert(PANEL_SMEM_BYTES + 256 <= 232448, "over the 227 KiB shared-memory limit");
+
+__device__ __forceinline__ int ld_acquire_gpu(const int* p) {
+  int v;
+  asm volatile("ld.acquire.gpu.global.s32 %0, [%1];\n" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_gpu(int* p, int v) {
+  asm volatile("st.release.gpu.global.s32 [%0], %1;\n" ::"l"(p), "r"(v) : "memory");
+}
+
+__global__ void __launch_bounds__(NTHREADS, 1) k_potrf_panel(SlotCtx c, int J, int nsr_max) {
+  extern __shared__ __align__(128) double smem[];
+  __shared__ __align__(8) uint64_t xbar[2];
+  int s, I;
+  if ((int)blockIdx.x < c.S) {
+    s = blockIdx.x;
+    I = J;
+  } else {
+    const int b = blockIdx.x - c.S, nd = nsr_max - J - 1;
+    s = b / nd;
+    I = J + 1 + b % nd;
+  }
+  if (!c.active[s]) return;
+  const int nb = c.nb[s];
+  const int j0 = 2 * J, j1 = 2 * J + 1;
+  if (2 * I >= nb) return;
+  const int N = c.n[s];
+  double* Lt = c.Lt + (long)s * c.tile_stride;
+  double* Kt = c.Kt + (long)s * c.tile_stride;
+  double* Xt = c.Xt + (long)s * c.tile_stride;
+  const bool two = (j1 < nb);
+  Frag2 f;
+  G2Pipe pipe;
+  if (threadIdx.x == 0) {
+    mbar_init(xbar, 1);
+    mbar_init(xbar + 1, 1);
+  }
+  pipe.init();   // fences the mbarrier inits and syncs
+  // L_I,panel = [C0 C1] X_JJ' with X_JJ = [[X00, 0], [X10, X11]]:  column j0 = C0 X00',  column j1 = C0 X10' + C1 X11'.
+  // Step 1 (k = j1, column-j1 warps only) needs X11 alone: it is fetched early into the extra tile behind the ring,
+  // and X00 / X10 for step 2 land in the third ring slot while step 1 runs.
+  double* sC = smem;                          // 4 tile images (ta, tb) at (2 * ta + tb) * TILE_ELEMS
+  double* sX1 = smem + 4 * TILE_ELEMS;        // X00, X10 (two tile columns) -- third ring slot
+  double* sXe = smem + G2_SMEM_ELEMS;         // X11 (or X00 when the panel has one tile column) -- outside the ring
+  const double* xe_src = two ? tile_ptr(Xt, j1, j1) : tile_ptr(Xt, j0, j0);
+  bool xe_issued = false;
+  if (I != J && threadIdx.x == 0 && ld_acquire_gpu(c.pflag + s) == J + 1) {   // already published: the common case
+    fence_proxy_async_all();
+    mbar_expect_tx(xbar, TILE_BYTES);
+    bulk_g2s(sXe, xe_src, TILE_BYTES, xbar);
+    xe_issued = true;
+  }
+  Acc2 acc;
+  acc.zero();
+  const int ti = 2 * I + f.ta, tj = j0 + f.tb;
+  const bool valid = (ti < nb) && (tj < nb) && (tj <= ti);
+  const double* ktile[2];
+  gemm2_pipeline_t<false, false, true>(
+      acc, smem, pipe, 0, j0,
+      [&](int k, int t) -> const double* { return (2 * I + t < nb) ? tile_ptr(Lt, 2 * I + t, k) : nullptr; },
+      [&](int k, int t) -> const double* { return (j0 + t < nb) ? tile_ptr(Lt, j0 + t, k) : nullptr; }, f,
+      [&](int e, int t) -> const double* {
+        const int a = 2 * I + e, b = j0 + t;
+        return (a < nb && b < nb && b <= a) ? tile_ptr(Kt, a, b) : nullptr;
+      },
+      ktile);
+  if (valid) {
+    const double* kt = ktile[f.ta] + f.tb * TILE_ELEMS;
+#pragma unroll
+    for (int mi = 0; mi < 8; ++mi)
+#pragma unroll
+      for (int ni = 0; ni < 4; ++ni) {
+        const double2 kv = *reinterpret_cast<const double2*>(kt + swz(f.row(mi), f.col(ni)));
+        acc.c[mi][ni][0] = kv.x - acc.c[mi][ni][0];
+        acc.c[mi][ni][1] = kv.y - acc.c[mi][ni][1];
+      }
+  }
+  __syncthreads();   // every warp has read its K tile: the ring is free
+  if (I != J) {
+    // ---- off-diagonal supertile: L_I,panel = C X_JJ' ----
+    if (threadIdx.x == 0) {
+      while (ld_acquire_gpu(c.pflag + s) != J + 1) __nanosleep(200);
+      fence_proxy_async_all();
+      if (!xe_issued) {
+        mbar_expect_tx(xbar, TILE_BYTES);
+        bulk_g2s(sXe, xe_src, TILE_BYTES, xbar);
+      }
+      if (two) {
+        mbar_expect_tx(xbar + 1, 2 * TILE_BYTES);
+        bulk_g2s(sX1, tile_ptr(Xt, j0, j0), TILE_BYTES, xbar + 1);
+        bulk_g2s(sX1 + TILE_ELEMS, tile_ptr(Xt, j1, j0), TILE_BYTES, xbar + 1);
+      }
+    }
+    if (ti < nb) store_acc2(sC + (2 * f.ta + f.tb) * TILE_ELEMS, acc, f);
+    __syncthreads();
+    acc.zero();
+    mbar_wait(xbar, 0);
+    if (ti < nb && f.tb == (two ? 1 : 0)) {         // step 1: C1 X11'  (one tile column: C0 X00')
+      const double* As = sC + (2 * f.ta + (two ? 1 : 0)) * TILE_ELEMS;
+#pragma unroll
+      for (int kh = 0; kh < 2; ++kh) mma_half<false, false>(acc, As + kh * HALF_ELEMS, sXe + kh * HALF_ELEMS, f);
+    }
+    if (two) {
+      mbar_wait(xbar + 1, 0);
+      if (ti < nb) {                                // step 2: C0 X00' -> column j0, C0 X10' -> column j1
+        const double* As = sC + (2 * f.ta) * TILE_ELEMS;
+        const double* Bs = sX1 + f.tb * TILE_ELEMS;
+#pragma unroll
+        for (int kh = 0; kh < 2; ++kh) mma_half<false, false>(acc, As + kh * HALF_ELEMS, Bs + kh * HALF_ELEMS, f);
+      }
+    }
+    if (ti < nb && tj < nb) store_acc2(tile_ptr(Lt, ti, tj), acc, f);
+    return;
+  }
+  // ---- diagonal 128x128 block (same arithmetic as k_potrf_update2) ----
+  double* a = smem;
+  double* inv = a + TB * LDA;
+  double* P0 = inv + TB * LDI;      // X00
+  double* P1 = P0 + TILE_ELEMS;     // C10, later M = L10 X00
+  double* P2 = P1 + TILE_ELEMS;     // C11, later X11
+  double* P3 = P2 + TILE_ELEMS;     // L10
+  double* dg = smem + G2_SMEM_ELEMS + TILE_ELEMS;
+  if (f.ta == 0 && f.tb == 0) {
+#pragma unroll
+    for (int mi = 0; mi < 8; ++mi)
+#pragma unroll
+      for (int ni = 0; ni < 4; ++ni) {
+        a[f.row(mi) * LDA + f.col(ni)] = acc.c[mi][ni][0];
+        a[f.row(mi) * LDA + f.col(ni) + 1] = acc.c[mi][ni][1];
+      }
+  } else if (two && f.ta == 1 && f.tb == 0) {
+    store_acc2(P1, acc, f);
+  } else if (two && f.ta == 1 && f.tb == 1) {
+    store_acc2(P2, acc, f);
+  }
+  potf2_trtri_64(a, inv, dg, j0 * TB, N, c.fail + s);
+  emit_diag(a, inv, dg, tile_ptr(Lt, j0, j0), tile_ptr(Xt, j0, j0), P0);
+  emit_logdet(dg, j0 * TB, N, c.logdet_part + s * c.nbmax + j0);
+  __syncthreads();
+  if (two) {
+    FragCoord fc;
+    {  // L10 = C10 X00'
+      Acc t;
+      t.zero();
+      mma_tile<false, false>(t, P1, P0, fc);
+      store_acc_swizzled(P3, t, fc);
+      store_acc_swizzled(tile_ptr(Lt, j1, j0), t, fc);
+    }
+    __syncthreads();
+    {  // C11' = C11 - L10 L10'
+      Acc t;
+      t.zero();
+      mma_tile<false, false>(t, P3, P3, fc);
+#pragma unroll
+      for (int mi = 0; mi < 2; ++mi)
+#pragma unroll
+        for (int ni = 0; ni < 4; ++ni)
+#pragma unroll
+          for (int e = 0; e < 2; ++e) {
+            const int m = fc.row(mi), n = fc.col(ni) + e;
+            a[m * LDA + n] = P2[swz(m, n)] - t.c[mi][ni][e];
+          }
+    }
+    potf2_trtri_64(a, inv, dg, j1 * TB, N, c.fail + s);
+    emit_diag(a, inv, dg, tile_ptr(Lt, j1, j1), tile_ptr(Xt, j1, j1), P2);
+    emit_logdet(dg, j1 * TB, N, c.logdet_part + s * c.nbmax + j1);
+    __syncthreads();
+    {  // M = L10 X00
+      Acc t;
+      t.zero();
+      mma_tile<false, true>(t, P3, P0, fc);
+      store_acc_swizzled(P1, t, fc);
+    }
+    __syncthreads();
+    {  // X10 = -X11 M
+      Acc t;
+      t.zero();
+      mma_tile<false, true>(t, P2, P1, fc);
+      store_acc_swizzled(tile_ptr(Xt, j1, j0), t, fc, -1.0);
+    }
+  }
+  // publish: every thread's global stores -> gpu scope, then one release store of the flag
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) st_release_gpu(c.pflag + s, J + 1);
+}
+
 // a'a from the augmented row of the factor (must run before k_trtri_* recycles Lt).  grid (S)
 __global__ void __launch_bounds__(NTHREADS) k_quad(SlotCtx c) {
   __shared__ double red[NTHREADS / 32];
@@ -357,7 +561,10 @@ __global__ void __launch_bounds__(NTHREADS) k_quad(SlotCtx c) {
     v[0] += a * a;
   }
   block_sum<1>(v, red);
-  if (threadIdx.x == 0) c.quad[s] = v[0];
+  if (threadIdx.x == 0) {
+    c.quad[s] = v[0];
+    c.pflag[s] = 0;   // the factorisation of this evaluation is complete: re-arm the panel flags
+  }
 }
 
 // ------------------------------------------------------------------------------------
@@ -680,7 +887,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_predict2(SlotCtx c, PredCtx p) 
       }
     }
   }
-  // column sums: over q (lanes sharing r), then over the two warps (wm = 0, 1) of a column slab
+  // column sums: over q (lanes sharing r), then over the two warps (ta = 0, 1) of a column slab
 #pragma unroll
   for (int ni = 0; ni < 4; ++ni)
 #pragma unroll
@@ -695,8 +902,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_predict2(SlotCtx c, PredCtx p) 
   if (f.q == 0) {
 #pragma unroll
     for (int ni = 0; ni < 4; ++ni) {
-      part[f.wm * 2 * TB + f.tb * TB + f.col(ni)] = csq[ni][0];
-      part[f.wm * 2 * TB + f.tb * TB + f.col(ni) + 1] = csq[ni][1];
+      part[f.ta * 2 * TB + f.tb * TB + f.col(ni)] = csq[ni][0];
+      part[f.ta * 2 * TB + f.tb * TB + f.col(ni) + 1] = csq[ni][1];
     }
   }
   __syncthreads();

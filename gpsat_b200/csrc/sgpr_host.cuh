@@ -62,12 +62,12 @@ static int sg_setup(gpsat_handle* h, const gpsat_sgpr_batch* sb, long long pmax,
   ENS(h->Kt2, (size_t)S * W.pl.ntmax * TILE_BYTES);
   ENS(h->quad2, (size_t)S * 8);
   ENS(h->logdet2, (size_t)S * W.pl.nbmax * 8);
-  ENS(h->fail2, (size_t)S * sizeof(int));
-  CK(cudaMemsetAsync(h->fail2.p, 0, (size_t)S * sizeof(int), st));
+  ENS(h->fail2, (size_t)2 * S * sizeof(int));
+  CK(cudaMemsetAsync(h->fail2.p, 0, (size_t)2 * S * sizeof(int), st));
   W.cb = cz;
   W.cb.nvar_override = -1.0;
   W.cb.Lt = (double*)h->Lt2.p; W.cb.Xt = (double*)h->Xt2.p; W.cb.Kt = (double*)h->Kt2.p;
-  W.cb.quad = (double*)h->quad2.p; W.cb.logdet_part = (double*)h->logdet2.p; W.cb.fail = (int*)h->fail2.p;
+  W.cb.quad = (double*)h->quad2.p; W.cb.logdet_part = (double*)h->logdet2.p; W.cb.fail = (int*)h->fail2.p; W.cb.pflag = (int*)h->fail2.p + S;
   ENS(h->sg_mm, (size_t)S * 4 * mm_tiles * TILE_BYTES);
   ENS(h->sg_mn, (size_t)S * 2 * mn_tiles * TILE_BYTES);
   ENS(h->sg_vec, (size_t)S * 8 * vlen * 8);

@@ -425,9 +425,10 @@ class Engine:
         _lib.check(self.lib.gpsat_set_profiling(self.h, int(on)))
 
     def get_profile(self):
-        v = [C.c_double() for _ in range(7)]
+        v = [C.c_double() for _ in range(9)]
         _lib.check(self.lib.gpsat_get_profile(self.h, *[C.byref(x) for x in v]))
-        k = ["ms_potrf", "ms_trtri", "ms_lauum", "ms_other", "flops_potrf", "flops_trtri", "flops_lauum"]
+        k = ["ms_potrf", "ms_trtri", "ms_lauum", "ms_other", "flops_potrf", "flops_trtri", "flops_lauum",
+             "ms_build", "ms_trace"]
         return {a: b.value for a, b in zip(k, v)}
 
 

@@ -207,11 +207,14 @@ int gpsat_debug_factor(gpsat_handle* h, const gpsat_batch* b, const double* thet
                        double* l_dense_dev, double* x_dense_dev, void* stream);
 
 /* counters: kernels launched by this library since the handle was created (bench: gpu_launches),
- * and CUDA-event time spent in the three DMMA factorisation phases when profiling is enabled */
+ * and CUDA-event time spent in the phases of an objective evaluation when profiling is enabled:
+ * potrf = k_potrf_* + k_quad (the batched Cholesky), trtri, lauum = k_lauum2, other = k_finalize2,
+ * build = k_build (kernel matrix), trace = k_grad_trace; flops_* = sum of N^3/3 over the slots evaluated */
 long long gpsat_launch_count(const gpsat_handle* h);
 int gpsat_set_profiling(gpsat_handle* h, int enabled);
 int gpsat_get_profile(gpsat_handle* h, double* ms_potrf, double* ms_trtri, double* ms_lauum,
-                      double* ms_other, double* flops_potrf, double* flops_trtri, double* flops_lauum);
+                      double* ms_other, double* flops_potrf, double* flops_trtri, double* flops_lauum,
+                      double* ms_build, double* ms_trace);
 
 /* Post-processing either side of the hot path.
  * gpsat_gaussian_smooth replaces gaussian_2d_weight (GPSat/postprocessing.py:22-52) as called by
