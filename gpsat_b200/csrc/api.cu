@@ -59,7 +59,6 @@ struct gpsat_handle {
   size_t host_ints_cap = 0;
   int max_slots = 0;         // 0: 4 slots per SM (GPSAT_MAX_SLOTS overrides)
   int n_groups = 3;          // slot groups / streams of the optimiser (GPSAT_GROUPS overrides)
-  int fused_panels = 1;      // Cholesky panels as one fused launch each (GPSAT_UNFUSED_POTRF=1: update + trsm launches)
   cudaStream_t gstream[8] = {};
   cudaEvent_t gevent[8] = {};
   cudaEvent_t ev_fork = nullptr;
@@ -118,10 +117,7 @@ extern "C" int gpsat_create(gpsat_handle** out, int device, size_t mem_budget_by
   size_t free_b = 0, total_b = 0;
   CK(cudaMemGetInfo(&free_b, &total_b));
   h->budget = mem_budget_bytes ? mem_budget_bytes : (size_t)(0.7 * (double)free_b);
-  if (const char* eu = getenv("GPSAT_UNFUSED_POTRF")) h->fused_panels = atoi(eu) ? 0 : 1;
   CK(cudaFuncSetAttribute(k_potrf_panel, cudaFuncAttributeMaxDynamicSharedMemorySize, PANEL_SMEM_BYTES));
-  CK(cudaFuncSetAttribute(k_potrf_update2, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM2_BYTES));
-  CK(cudaFuncSetAttribute(k_potrf_trsm2, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM2_BYTES));
   CK(cudaFuncSetAttribute(k_trtri_pass1, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM2_BYTES));
   CK(cudaFuncSetAttribute(k_trtri_pass2, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM2_BYTES));
   CK(cudaFuncSetAttribute(k_lauum2, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM2_BYTES));
@@ -313,17 +309,8 @@ static int run_round_flags(gpsat_handle* h, const SlotCtx& c, int nbm, int flags
   }
   if (prof) cudaEventRecord(next_event(h), st);
   for (int J = 0; J < nsr; ++J) {
-    if (h->fused_panels) {
-      k_potrf_panel<<<c.S + c.S * (nsr - J - 1), NTHREADS, PANEL_SMEM_BYTES, st>>>(c, J, nsr);
-      ++h->launches;
-      continue;
-    }
-    k_potrf_update2<<<dim3(nsr - J, c.S), NTHREADS, SMEM2_BYTES, st>>>(c, J);
+    k_potrf_panel<<<c.S + c.S * (nsr - J - 1), NTHREADS, PANEL_SMEM_BYTES, st>>>(c, J, nsr);
     ++h->launches;
-    if (J + 1 < nsr) {
-      k_potrf_trsm2<<<dim3(nsr - J - 1, c.S), NTHREADS, SMEM2_BYTES, st>>>(c, J);
-      ++h->launches;
-    }
   }
   k_quad<<<c.S, NTHREADS, 0, st>>>(c);
   ++h->launches;
@@ -971,6 +958,14 @@ extern "C" int gpsat_microbench(int device, int which, int param, int nk, double
     if (which == 2) r = time_launch([&] { k_dmma_chain<4><<<grid, 256>>>(iters, buf); }, &ms);
     if (which == 3) r = time_launch([&] { k_dmma_chain<8><<<grid, 256>>>(iters, buf); }, &ms);
     *tflops_out = 2.0 * 256 * nch * (double)iters * 8 * grid / (ms * 1e-3) / 1e12;
+  } else if (which == 30) {   // microseconds per 128x128 diagonal block (one CTA per SM, nk repetitions)
+    CK(cudaMalloc(&buf, (size_t)nsm * (6 * TILE_BYTES + 64)));
+    CK(cudaMemset(buf, 0, (size_t)nsm * (6 * TILE_BYTES + 64)));
+    double* ld = buf + (size_t)nsm * 6 * TILE_ELEMS;
+    int* fl = (int*)(ld + 2 * nsm);
+    CK(cudaFuncSetAttribute(k_diag_bench, cudaFuncAttributeMaxDynamicSharedMemorySize, PANEL_SMEM_BYTES));
+    r = time_launch([&] { k_diag_bench<<<nsm, NTHREADS, PANEL_SMEM_BYTES>>>(nk, buf, fl, ld); }, &ms);
+    *tflops_out = ms * 1e3 / nk;
   } else if (which == 20 || which == 21) {
     CK(cudaMalloc(&buf, 64));
     const int grid = nsm * 4;

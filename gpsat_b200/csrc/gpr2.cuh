@@ -25,10 +25,10 @@
 namespace gpsat {
 
 constexpr int NG = MAXP;                              // gradient partials per tile
-// diagonal-block workspace of k_potrf_update2: a[64][65] + inv[64][68] + 4 tiles
-constexpr int LDA = 65;
+// diagonal-block workspace (diag_block_128): a[64][68] + inv[64][68] + 4 tiles
+constexpr int LDA = 68;
 constexpr int LDI = 68;
-constexpr int DIAG_ELEMS = TB * LDA + TB * LDI + 4 * TILE_ELEMS;            // 24896
+constexpr int DIAG_ELEMS = TB * LDA + TB * LDI + 4 * TILE_ELEMS;            // 25088 (diag_block_128 workspace)
 constexpr int G2_AUX = 2 * MAXD * TB + 2 * TB + 64;
 constexpr int SMEM2_ELEMS = (DIAG_ELEMS > G2_SMEM_ELEMS ? DIAG_ELEMS : G2_SMEM_ELEMS) + G2_AUX;
 constexpr int SMEM2_BYTES = SMEM2_ELEMS * 8;
@@ -136,37 +136,87 @@ __global__ void __launch_bounds__(256, 4) k_build(SlotCtx c) {
 
 // ------------------------------------------------------------------------------------
 // 64x64 diagonal block: Cholesky + triangular inverse in shared memory
-// a: [64][65] (lower part valid), inv: [64][68], dg: [64].  All NTHREADS threads call.
+// a: [64][LDA] (lower part valid), inv: [64][LDI], dg: [64].  All NTHREADS (8 warps) call.
 // Global indices >= N (augmented row and padding) get a forced unit pivot.
+//
+// Blocked by 8: warp w owns block row w.  Left-looking step jb: every warp w >= jb forms
+// U = A[w][jb] - sum_kb L[w][kb] L[jb][kb]' with DMMA (register accumulator); warp jb factorises its 8x8 block
+// and inverts it with every lane doing the same 8x8 arithmetic in registers (no shuffles on the critical
+// chain); the warps below multiply by the inverse (U reaches the A-fragment layout by two shuffles).
+// The triangular inverse is then swept by block columns, one warp per column, without block barriers:
+// X[ib][jb] = -X[ib][ib] (sum_kb L[ib][kb] X[kb][jb]).   (The previous element-wise version took 60 us per
+// 64x64 block and was the critical path of every Cholesky panel; this one is ~8x shorter.)
 // ------------------------------------------------------------------------------------
+__device__ __forceinline__ void chol8_inv(double* blk, double* invblk, double* dg8, int gbase, int N,
+                                          int* fail_flag, int lane) {
+  bool bad = false;
+#include "chol8.inc"
+  if (bad && lane == 0) *fail_flag = 1;
+}
+
 __device__ __forceinline__ void potf2_trtri_64(double* a, double* inv, double* dg, int g0, int N, int* fail_flag) {
-  const int tid = threadIdx.x;
-  const int rr = tid & 63, cg = tid >> 6;
-  for (int c = 0; c < TB; ++c) {
-    __syncthreads();
-    double d = a[c * LDA + c];
-    if (g0 + c >= N) d = 1.0;
-    if (!(d > 0.0)) {
-      if (tid == 0) *fail_flag = 1;
-      d = 1.0;
-    }
-    const double piv = sqrt(d);
-    if (tid < TB) {
-      if (tid > c) a[tid * LDA + c] *= (1.0 / piv);
-      else if (tid == c) dg[c] = piv;
-    }
-    __syncthreads();
-    const double lrc = a[rr * LDA + c];
-    for (int cc = c + 1 + cg; cc <= rr; cc += 4) a[rr * LDA + cc] -= lrc * a[cc * LDA + c];
-  }
+  const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5, q = lane >> 2, r = lane & 3;
+  for (int t = tid; t < TB * LDI; t += NTHREADS) inv[t] = 0.0;
   __syncthreads();
-  const int col = tid >> 2, part = tid & 3;
-  for (int r = 0; r < TB; ++r) {
-    double sum = 0.0;
-    for (int k = part; k < r; k += 4) sum += a[r * LDA + k] * inv[k * LDI + col];
-    sum += __shfl_xor_sync(0xffffffffu, sum, 1);
-    sum += __shfl_xor_sync(0xffffffffu, sum, 2);
-    if (part == 0) inv[r * LDI + col] = (r >= col) ? (((r == col) ? 1.0 : 0.0) - sum) / dg[r] : 0.0;
+  for (int jb = 0; jb < 8; ++jb) {
+    double c0 = 0.0, c1 = 0.0;
+    if (w >= jb) {
+      c0 = a[(8 * w + q) * LDA + 8 * jb + 2 * r];
+      c1 = a[(8 * w + q) * LDA + 8 * jb + 2 * r + 1];
+      for (int kb = 0; kb < jb; ++kb) {
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const double af = -a[(8 * w + q) * LDA + 8 * kb + 4 * h + r];
+          const double bf = a[(8 * jb + q) * LDA + 8 * kb + 4 * h + r];
+          dmma884(c0, c1, af, bf);
+        }
+      }
+    }
+    if (w == jb) {
+      a[(8 * w + q) * LDA + 8 * jb + 2 * r] = c0;
+      a[(8 * w + q) * LDA + 8 * jb + 2 * r + 1] = c1;
+      __syncwarp();
+      chol8_inv(a + (8 * jb) * LDA + 8 * jb, inv + (8 * jb) * LDI + 8 * jb, dg + 8 * jb, g0 + 8 * jb, N, fail_flag,
+                lane);
+    }
+    __syncthreads();   // the inverse of the diagonal 8x8 block is visible
+    if (w > jb) {      // L[w][jb] = U inv(L_jj)'
+      double o0 = 0.0, o1 = 0.0;
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int src = q * 4 + 2 * h + (r >> 1);
+        const double t0 = __shfl_sync(0xffffffffu, c0, src), t1 = __shfl_sync(0xffffffffu, c1, src);
+        const double af = (r & 1) ? t1 : t0;                                   // U[q][4h + r]
+        const double bf = inv[(8 * jb + q) * LDI + 8 * jb + 4 * h + r];        // B[k][n] = invL[n][k]
+        dmma884(o0, o1, af, bf);
+      }
+      a[(8 * w + q) * LDA + 8 * jb + 2 * r] = o0;
+      a[(8 * w + q) * LDA + 8 * jb + 2 * r + 1] = o1;
+    }
+    __syncthreads();   // block column jb of L is final
+  }
+  // triangular inverse: warp w sweeps block column w
+  for (int ib = w + 1; ib < 8; ++ib) {
+    double t0 = 0.0, t1 = 0.0;
+    for (int kb = w; kb < ib; ++kb) {
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const double af = a[(8 * ib + q) * LDA + 8 * kb + 4 * h + r];           // L[ib][kb]
+        const double bf = inv[(8 * kb + 4 * h + r) * LDI + 8 * w + q];          // X[kb][w]
+        dmma884(t0, t1, af, bf);
+      }
+    }
+    double o0 = 0.0, o1 = 0.0;
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const double af = inv[(8 * ib + q) * LDI + 8 * ib + 4 * h + r];           // X[ib][ib]
+      const int src = (4 * h + r) * 4 + (q >> 1);
+      const double u0 = __shfl_sync(0xffffffffu, t0, src), u1 = __shfl_sync(0xffffffffu, t1, src);
+      const double bf = (q & 1) ? u1 : u0;                                      // T[4h + r][q]
+      dmma884(o0, o1, af, bf);
+    }
+    inv[(8 * ib + q) * LDI + 8 * w + 2 * r] = -o0;
+    inv[(8 * ib + q) * LDI + 8 * w + 2 * r + 1] = -o1;
     __syncwarp();
   }
   __syncthreads();
@@ -195,92 +245,38 @@ __device__ __forceinline__ void emit_logdet(const double* dg, int g0, int N, dou
 }
 
 // ------------------------------------------------------------------------------------
-// potrf panel J (tiles j0 = 2J, j1 = 2J+1), part 1:
-//   C_{i,j} = K_aug(i,j) - sum_{k<j0} L_ik L_jk'  for the 2x2 tile group of supertile row I >= J.
-// The diagonal CTA (I == J) factorises the 128x128 block: L00, L10, L11 -> Lt, X00, X10, X11 -> Xt.
-// grid (nsr_max - J, S)
+// 128x128 diagonal block of a panel, entirely in shared memory.  In: ws[0 ..) = C00 as a[64][LDA] (lower part),
+// ws + DIAG_P1 = C10, ws + DIAG_P2 = C11 (tile images).  Out (global, tile images): L00, L10, L11 and
+// X = L^-1: X00, X10, X11; log-determinant partials ld[0], ld[1].  `two` = the block has a second tile row.
+// All NTHREADS threads call; ends with the global stores issued (no trailing barrier).
 // ------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(NTHREADS, 1) k_potrf_update2(SlotCtx c, int J) {
-  extern __shared__ __align__(128) double smem[];
-  const int s = blockIdx.y;
-  if (!c.active[s]) return;
-  const int nb = c.nb[s];
-  const int I = J + blockIdx.x;
-  const int j0 = 2 * J, j1 = 2 * J + 1;
-  if (2 * I >= nb) return;
-  const int N = c.n[s];
-  double* Lt = c.Lt + (long)s * c.tile_stride;
-  double* Kt = c.Kt + (long)s * c.tile_stride;
-  Frag2 f;
-  G2Pipe pipe;
-  pipe.init();
-  Acc2 acc;
-  acc.zero();
-  const int ti = 2 * I + f.ta, tj = j0 + f.tb;
-  const bool valid = (ti < nb) && (tj < nb) && (tj <= ti);
-  // the four K_aug tiles of this group ride through the ring behind the last k-slices (tail), so the
-  // epilogue reads them from shared memory instead of waiting on 32 dependent global loads per thread
-  const double* ktile[2];
-  gemm2_pipeline_t<false, false, true>(
-      acc, smem, pipe, 0, j0,
-      [&](int k, int t) -> const double* { return (2 * I + t < nb) ? tile_ptr(Lt, 2 * I + t, k) : nullptr; },
-      [&](int k, int t) -> const double* { return (j0 + t < nb) ? tile_ptr(Lt, j0 + t, k) : nullptr; }, f,
-      [&](int e, int t) -> const double* {
-        const int a = 2 * I + e, b = j0 + t;
-        return (a < nb && b < nb && b <= a) ? tile_ptr(Kt, a, b) : nullptr;
-      },
-      ktile);
-  if (valid) {
-    const double* kt = ktile[f.ta] + f.tb * TILE_ELEMS;
-#pragma unroll
-    for (int mi = 0; mi < 8; ++mi)
-#pragma unroll
-      for (int ni = 0; ni < 4; ++ni) {
-        const double2 kv = *reinterpret_cast<const double2*>(kt + swz(f.row(mi), f.col(ni)));
-        acc.c[mi][ni][0] = kv.x - acc.c[mi][ni][0];
-        acc.c[mi][ni][1] = kv.y - acc.c[mi][ni][1];
-      }
-  }
-  if (I != J) {
-    if (valid) store_acc2(tile_ptr(Lt, ti, tj), acc, f);
-    return;
-  }
-  // ---- diagonal 128x128 block ----
-  double* Xt = c.Xt + (long)s * c.tile_stride;
-  double* a = smem;
-  double* inv = a + TB * LDA;
-  double* P0 = inv + TB * LDI;      // X00
-  double* P1 = P0 + TILE_ELEMS;     // C10, later M = L10 X00
-  double* P2 = P1 + TILE_ELEMS;     // C11, later X11
-  double* P3 = P2 + TILE_ELEMS;     // L10
-  double* dg = smem + (SMEM2_ELEMS - G2_AUX);
-  const bool two = (j1 < nb);
-  __syncthreads();   // every warp has read its K tile: the ring is free
-  if (f.ta == 0 && f.tb == 0) {
-#pragma unroll
-    for (int mi = 0; mi < 8; ++mi)
-#pragma unroll
-      for (int ni = 0; ni < 4; ++ni) {
-        a[f.row(mi) * LDA + f.col(ni)] = acc.c[mi][ni][0];
-        a[f.row(mi) * LDA + f.col(ni) + 1] = acc.c[mi][ni][1];
-      }
-  } else if (two && f.ta == 1 && f.tb == 0) {
-    store_acc2(P1, acc, f);
-  } else if (two && f.ta == 1 && f.tb == 1) {
-    store_acc2(P2, acc, f);
-  }
-  potf2_trtri_64(a, inv, dg, j0 * TB, N, c.fail + s);
-  emit_diag(a, inv, dg, tile_ptr(Lt, j0, j0), tile_ptr(Xt, j0, j0), P0);
-  emit_logdet(dg, j0 * TB, N, c.logdet_part + s * c.nbmax + j0);
+constexpr int DIAG_INV = TB * LDA;
+constexpr int DIAG_P0 = DIAG_INV + TB * LDI;
+constexpr int DIAG_P1 = DIAG_P0 + TILE_ELEMS;
+constexpr int DIAG_P2 = DIAG_P1 + TILE_ELEMS;
+constexpr int DIAG_P3 = DIAG_P2 + TILE_ELEMS;
+__device__ __forceinline__ void diag_block_128(double* ws, double* dg, bool two, int j0, int N, int* fail_flag,
+                                               double* gL00, double* gL10, double* gL11, double* gX00, double* gX10,
+                                               double* gX11, double* ld) {
+  double* a = ws;
+  double* inv = ws + DIAG_INV;
+  double* P0 = ws + DIAG_P0;      // X00
+  double* P1 = ws + DIAG_P1;      // C10, later M = L10 X00
+  double* P2 = ws + DIAG_P2;      // C11, later X11
+  double* P3 = ws + DIAG_P3;      // L10
+  potf2_trtri_64(a, inv, dg, j0 * TB, N, fail_flag);
+  emit_diag(a, inv, dg, gL00, gX00, P0);
+  emit_logdet(dg, j0 * TB, N, ld);
   __syncthreads();
   if (!two) return;
+  const int j1 = j0 + 1;
   FragCoord fc;
   {  // L10 = C10 X00'
     Acc t;
     t.zero();
     mma_tile<false, false>(t, P1, P0, fc);
     store_acc_swizzled(P3, t, fc);
-    store_acc_swizzled(tile_ptr(Lt, j1, j0), t, fc);
+    store_acc_swizzled(gL10, t, fc);
   }
   __syncthreads();
   {  // C11' = C11 - L10 L10'
@@ -297,9 +293,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_potrf_update2(SlotCtx c, int J)
           a[m * LDA + n] = P2[swz(m, n)] - t.c[mi][ni][e];
         }
   }
-  potf2_trtri_64(a, inv, dg, j1 * TB, N, c.fail + s);
-  emit_diag(a, inv, dg, tile_ptr(Lt, j1, j1), tile_ptr(Xt, j1, j1), P2);
-  emit_logdet(dg, j1 * TB, N, c.logdet_part + s * c.nbmax + j1);
+  potf2_trtri_64(a, inv, dg, j1 * TB, N, fail_flag);
+  emit_diag(a, inv, dg, gL11, gX11, P2);
+  emit_logdet(dg, j1 * TB, N, ld + 1);
   __syncthreads();
   {  // M = L10 X00
     Acc t;
@@ -312,42 +308,14 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_potrf_update2(SlotCtx c, int J)
     Acc t;
     t.zero();
     mma_tile<false, true>(t, P2, P1, fc);
-    store_acc_swizzled(tile_ptr(Xt, j1, j0), t, fc, -1.0);
+    store_acc_swizzled(gX10, t, fc, -1.0);
   }
 }
 
-// potrf panel J, part 2: L_{I,panel} = C_{I,panel} * Ldiag^-T  for I > J.   grid (nsr_max - J - 1, S)
-__global__ void __launch_bounds__(NTHREADS, 1) k_potrf_trsm2(SlotCtx c, int J) {
-  extern __shared__ __align__(128) double smem[];
-  const int s = blockIdx.y;
-  if (!c.active[s]) return;
-  const int nb = c.nb[s];
-  const int I = J + 1 + blockIdx.x;
-  const int j0 = 2 * J;
-  if (2 * I >= nb) return;
-  double* Lt = c.Lt + (long)s * c.tile_stride;
-  double* Xt = c.Xt + (long)s * c.tile_stride;
-  Frag2 f;
-  G2Pipe pipe;
-  pipe.init();
-  Acc2 acc;
-  acc.zero();
-  const int kend = (j0 + 1 < nb) ? 2 : 1;
-  gemm2_pipeline<false, false>(
-      acc, smem, pipe, 0, kend,
-      [&](int k, int t) -> const double* { return (2 * I + t < nb) ? tile_ptr(Lt, 2 * I + t, j0 + k) : nullptr; },
-      [&](int k, int t) -> const double* {
-        return (t >= k && j0 + t < nb) ? tile_ptr(Xt, j0 + t, j0 + k) : nullptr;
-      },
-      f);
-  const int ti = 2 * I + f.ta, tj = j0 + f.tb;
-  if (ti < nb && tj < nb) store_acc2(tile_ptr(Lt, ti, tj), acc, f);
-}
-
 // ------------------------------------------------------------------------------------
-// Fused potrf panel J (replaces k_potrf_update2 + k_potrf_trsm2: one launch per panel, the C block never
+// Fused potrf panel J (update + triangular solve in one launch per panel: the C block never
 // goes through global memory).  1-D grid, diagonal CTAs first:
-//   blocks [0, S)            : slot b, supertile row I = J: update + 128x128 factorisation (as k_potrf_update2),
+//   blocks [0, S)            : slot b, supertile row I = J: update + 128x128 factorisation (diag_block_128),
 //                              then publish pflag[s] = J + 1 (release)
 //   blocks [S, S + S * nd)   : nd = nsr_max - J - 1; slot (b - S) / nd, row I = J + 1 + (b - S) % nd:
 //                              C = K - sum_k L_Ik L_Jk' in registers -> shared memory (4 tile images), wait for the
@@ -474,73 +442,24 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_potrf_panel(SlotCtx c, int J, i
     if (ti < nb && tj < nb) store_acc2(tile_ptr(Lt, ti, tj), acc, f);
     return;
   }
-  // ---- diagonal 128x128 block (same arithmetic as k_potrf_update2) ----
-  double* a = smem;
-  double* inv = a + TB * LDA;
-  double* P0 = inv + TB * LDI;      // X00
-  double* P1 = P0 + TILE_ELEMS;     // C10, later M = L10 X00
-  double* P2 = P1 + TILE_ELEMS;     // C11, later X11
-  double* P3 = P2 + TILE_ELEMS;     // L10
+  // ---- diagonal 128x128 block ----
   double* dg = smem + G2_SMEM_ELEMS + TILE_ELEMS;
   if (f.ta == 0 && f.tb == 0) {
 #pragma unroll
     for (int mi = 0; mi < 8; ++mi)
 #pragma unroll
       for (int ni = 0; ni < 4; ++ni) {
-        a[f.row(mi) * LDA + f.col(ni)] = acc.c[mi][ni][0];
-        a[f.row(mi) * LDA + f.col(ni) + 1] = acc.c[mi][ni][1];
+        smem[f.row(mi) * LDA + f.col(ni)] = acc.c[mi][ni][0];
+        smem[f.row(mi) * LDA + f.col(ni) + 1] = acc.c[mi][ni][1];
       }
   } else if (two && f.ta == 1 && f.tb == 0) {
-    store_acc2(P1, acc, f);
+    store_acc2(smem + DIAG_P1, acc, f);
   } else if (two && f.ta == 1 && f.tb == 1) {
-    store_acc2(P2, acc, f);
+    store_acc2(smem + DIAG_P2, acc, f);
   }
-  potf2_trtri_64(a, inv, dg, j0 * TB, N, c.fail + s);
-  emit_diag(a, inv, dg, tile_ptr(Lt, j0, j0), tile_ptr(Xt, j0, j0), P0);
-  emit_logdet(dg, j0 * TB, N, c.logdet_part + s * c.nbmax + j0);
-  __syncthreads();
-  if (two) {
-    FragCoord fc;
-    {  // L10 = C10 X00'
-      Acc t;
-      t.zero();
-      mma_tile<false, false>(t, P1, P0, fc);
-      store_acc_swizzled(P3, t, fc);
-      store_acc_swizzled(tile_ptr(Lt, j1, j0), t, fc);
-    }
-    __syncthreads();
-    {  // C11' = C11 - L10 L10'
-      Acc t;
-      t.zero();
-      mma_tile<false, false>(t, P3, P3, fc);
-#pragma unroll
-      for (int mi = 0; mi < 2; ++mi)
-#pragma unroll
-        for (int ni = 0; ni < 4; ++ni)
-#pragma unroll
-          for (int e = 0; e < 2; ++e) {
-            const int m = fc.row(mi), n = fc.col(ni) + e;
-            a[m * LDA + n] = P2[swz(m, n)] - t.c[mi][ni][e];
-          }
-    }
-    potf2_trtri_64(a, inv, dg, j1 * TB, N, c.fail + s);
-    emit_diag(a, inv, dg, tile_ptr(Lt, j1, j1), tile_ptr(Xt, j1, j1), P2);
-    emit_logdet(dg, j1 * TB, N, c.logdet_part + s * c.nbmax + j1);
-    __syncthreads();
-    {  // M = L10 X00
-      Acc t;
-      t.zero();
-      mma_tile<false, true>(t, P3, P0, fc);
-      store_acc_swizzled(P1, t, fc);
-    }
-    __syncthreads();
-    {  // X10 = -X11 M
-      Acc t;
-      t.zero();
-      mma_tile<false, true>(t, P2, P1, fc);
-      store_acc_swizzled(tile_ptr(Xt, j1, j0), t, fc, -1.0);
-    }
-  }
+  diag_block_128(smem, dg, two, j0, N, c.fail + s, tile_ptr(Lt, j0, j0), two ? tile_ptr(Lt, j1, j0) : nullptr,
+                 two ? tile_ptr(Lt, j1, j1) : nullptr, tile_ptr(Xt, j0, j0), two ? tile_ptr(Xt, j1, j0) : nullptr,
+                 two ? tile_ptr(Xt, j1, j1) : nullptr, c.logdet_part + s * c.nbmax + j0);
   // publish: every thread's global stores -> gpu scope, then one release store of the flag
   __threadfence();
   __syncthreads();

@@ -3,6 +3,7 @@
 #pragma once
 #include "gemm_core.cuh"
 #include "gemm2.cuh"
+#include "gpr2.cuh"
 
 namespace gpsat {
 
@@ -96,6 +97,27 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_gemm2_bench(const double* tiles
 #pragma unroll
     for (int ni = 0; ni < 4; ++ni) s += acc.c[mi][ni][0] + acc.c[mi][ni][1];
   if (s == 12345.678) out[0] = s;
+}
+
+// the 128x128 diagonal-block routine of the Cholesky panels in isolation: every CTA factorises `reps` times a
+// diagonally dominant block it builds in shared memory; out[0..] receives scratch tiles
+__global__ void __launch_bounds__(NTHREADS, 1) k_diag_bench(int reps, double* scratch, int* fail, double* ld) {
+  extern __shared__ __align__(128) double smem[];
+  double* dg = smem + G2_SMEM_ELEMS + TILE_ELEMS;
+  double* g = scratch + (long)blockIdx.x * 6 * TILE_ELEMS;
+  for (int it = 0; it < reps; ++it) {
+    __syncthreads();
+    for (int t = threadIdx.x; t < TILE_ELEMS; t += NTHREADS) {
+      const int r = t >> 6, cc = t & 63;
+      const double off = 0.01 / (1.0 + abs(r - cc));
+      smem[r * LDA + cc] = (r == cc) ? 2.0 : off;
+      smem[DIAG_P1 + swz(r, cc)] = 0.005 / (1.0 + abs(r + 64 - cc));
+      smem[DIAG_P2 + swz(r, cc)] = (r == cc) ? 2.0 : off;
+    }
+    __syncthreads();
+    diag_block_128(smem, dg, true, 0, 1 << 30, fail + blockIdx.x, g, g + TILE_ELEMS, g + 2 * TILE_ELEMS,
+                   g + 3 * TILE_ELEMS, g + 4 * TILE_ELEMS, g + 5 * TILE_ELEMS, ld + 2 * blockIdx.x);
+  }
 }
 
 // 64x64 core (gemm_core.cuh), same modes

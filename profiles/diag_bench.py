@@ -1,0 +1,12 @@
+"""Time the 128x128 diagonal-block routine of the Cholesky panels in isolation (run via gpurun)."""
+import ctypes as C
+import os
+import sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from gpsat_b200 import build, _lib
+build.build()
+lib = _lib.load()
+v = C.c_double()
+for reps in (10, 50):
+    assert lib.gpsat_microbench(0, 30, 0, reps, C.byref(v)) == 0, lib.gpsat_last_error()
+    print(f"diag block 128x128 (potf2 + inverse + 5 tile products), {reps} reps: {v.value:.1f} us per block")

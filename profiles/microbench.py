@@ -27,4 +27,5 @@ for mode, nm in ((1, "dmma only"), (2, "dfma only"), (3, "dmma + dfma")):
     out[f"pipe mix {nm} (ms)"] = run(20, mode, 4000)
 for kid, nm in enumerate(("Matern32", "Matern52", "Matern12", "RBF")):
     out[f"kernel eval rate {nm} (G entries/s)"] = run(21, kid, 2000)
+out["diag block 128x128 potrf+inverse (us per block per CTA)"] = run(30, 0, 50)
 print(json.dumps(out, indent=1))
