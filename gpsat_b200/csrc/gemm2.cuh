@@ -107,16 +107,23 @@ __device__ __forceinline__ void mma_half(Acc2& acc, const double* __restrict__ A
 // Ring state of one CTA: mbarriers in shared memory + the number of slices that went through the ring so far
 // (stage and phase parity of slice n are n % G2_STAGES and (n / G2_STAGES) & 1), so several pipelines can run
 // back to back in one kernel.  init() must be called by all threads once, before the first pipeline.
+// done[s] counts the warps that have finished reading the slice in ring slot s.
 struct G2Pipe {
   uint64_t* full;
+  int* done;
   uint32_t count;
   __device__ __forceinline__ void init() {
     __shared__ __align__(8) uint64_t bars[G2_STAGES];
+    __shared__ int cnt[G2_STAGES];
     full = bars;
+    done = cnt;
     count = 0;
     if (threadIdx.x == 0) {
 #pragma unroll
-      for (int s = 0; s < G2_STAGES; ++s) mbar_init(bars + s, 1);
+      for (int s = 0; s < G2_STAGES; ++s) {
+        mbar_init(bars + s, 1);
+        cnt[s] = 0;
+      }
       fence_mbar_init();
     }
     __syncthreads();
@@ -133,6 +140,10 @@ struct NoTail {
 // a_of(k, t) / b_of(k, t), t in {0,1}: global pointer of the tile or nullptr (structurally zero /
 // out of range: the copy and the products that would use it are skipped; nullness must be
 // CTA-uniform).  smem: G2_SMEM_ELEMS doubles.
+// There is no block barrier inside the loop: a warp waits only for the mbarrier of the slice it is about to read;
+// when it is done with a slice it bumps the slot's counter, and the LAST of the 8 warps to do so issues the TMA
+// copies of the slice that reuses the slot (so warps may drift up to two slices apart and the DMMA pipes never
+// drain at slice boundaries).
 // TAIL: after the last k-slice two more ring slots are filled with whole tiles tail_of(e, t), e, t in {0,1}
 // (e.g. the C tiles an epilogue needs), fetched while the last slices are being multiplied; slot e lands in
 // tail[e] (tile t at tail[e] + t * TILE_ELEMS, missing tiles are not touched).  Without TAIL the call ends with
@@ -144,7 +155,7 @@ __device__ __forceinline__ void gemm2_pipeline_t(Acc2& acc, double* smem, G2Pipe
   const int nsl = (kend > kbeg) ? 2 * (kend - kbeg) : 0;   // 32-deep slices
   const int ntot = nsl + (TAIL ? 2 : 0);
   if (ntot == 0) return;
-  auto issue = [&](int sl) {    // thread 0 only
+  auto issue = [&](int sl) {    // one thread
     const uint32_t n = p.count + sl;
     double* st = smem + p.stage(n) * G2_STAGE_ELEMS;
     uint64_t* bar = p.full + p.stage(n);
@@ -179,8 +190,18 @@ __device__ __forceinline__ void gemm2_pipeline_t(Acc2& acc, double* smem, G2Pipe
       const double* st = smem + p.stage(n) * G2_STAGE_ELEMS;
       mma_half<TA, TBm>(acc, st + f.ta * HALF_ELEMS, st + (2 + f.tb) * HALF_ELEMS, f);
     }
-    __syncthreads();         // everyone is done with this ring slot
-    if (threadIdx.x == 0 && sl + G2_STAGES < ntot) issue(sl + G2_STAGES);
+    if (sl + G2_STAGES < ntot) {
+      // this warp's fragment loads of the slice have all returned (the DMMAs consumed them)
+      __syncwarp();
+      if (f.lane == 0) {
+        int* cnt = p.done + p.stage(n);
+        if (atomicAdd(cnt, 1) == NTHREADS / 32 - 1) {   // last warp out refills the slot
+          atomicExch(cnt, 0);
+          __threadfence_block();
+          issue(sl + G2_STAGES);
+        }
+      }
+    }
   }
   if (TAIL) {
 #pragma unroll
@@ -188,6 +209,8 @@ __device__ __forceinline__ void gemm2_pipeline_t(Acc2& acc, double* smem, G2Pipe
       p.wait(p.count + nsl + e);
       tail[e] = smem + p.stage(p.count + nsl + e) * G2_STAGE_ELEMS;
     }
+  } else {
+    __syncthreads();
   }
   p.count += ntot;
 }
