@@ -39,7 +39,7 @@ def parse():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="c3", choices=["c3", "c1", "c5", "tiny"])
+    ap.add_argument("--workload", default="c3", choices=["c3", "c1", "c4", "c5", "tiny"])
     ap.add_argument("--experts-per-step", type=int, default=1024, help="experts per rank per step")
     ap.add_argument("--cpu-sample", type=int, default=1, help="experts timed by the cpu_baseline leg")
     ap.add_argument("--no-cpu-baseline", action="store_true")

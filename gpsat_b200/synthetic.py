@@ -106,6 +106,20 @@ def workload(name="c3", n_experts=None, seed=SEED):
                     optimise=True,
                     describe="inline_example shape: 200 km expert lattice, ~400-600 obs per expert, "
                              "optimise + predict on the 5 km grid within 200 km")
+    if name == "c4":
+        # 5 km-resolution expert grid (the full run has ~1e5 experts; a step takes a lattice sample of them), dense
+        # along-track observations: variable N up to ~8k per expert, full optimisation
+        E = 4096 if n_experts is None else n_experts
+        table = observations(rng, radius_cells=60, days=range(18316, 18337), density_lo=0.25, density_hi=0.98,
+                             n_sat=8)
+        experts = expert_lattice(E)            # every 10th point of the 5 km grid: the density range is sampled
+        half = float(np.abs(experts[:, :2]).max()) + 10_000.0
+        return dict(name="c4", table=table, table_cols=["x", "y", "t", "obs"], experts=experts,
+                    expert_cols=["x", "y", "t"], pred=pred_grid(half, 2_500.0), pred_cols=["x", "y"], max_dist=5_000.0,
+                    local_select=LOCAL_SELECT, model=MODEL_C3, coords_col=["x", "y", "t"], obs_col="obs",
+                    optimise=True,
+                    describe="5 km expert grid, 300 km radius / 9-day window, dense tracks: variable N up to ~8k obs "
+                             "per expert, Matern32 ARD (x,y,t), L-BFGS optimise + predict within 5 km")
     if name == "c5":
         # sparse path: GPflowSGPRModel-equivalent, 500 inducing points per expert, N ~ 2k-10k, 50 km expert lattice
         E = 8192 if n_experts is None else n_experts

@@ -411,6 +411,48 @@ def test_large_experts_objective_gradient_predict(eng):
         np.testing.assert_allclose(fv[e * P:(e + 1) * P], v, rtol=1e-6, atol=1e-10)
 
 
+def test_c4_size_expert_8000_obs(eng):
+    """BASELINE configs[3]: variable N up to 8k observations per expert.  N = 8000 (+ a ragged N = 3 neighbour in the
+    same batch): objective against the oracle at 1e-8, predictions at the fixed-parameter tolerance, and the
+    size-independent property that the gradient matches central finite differences of the CUDA objective itself."""
+    rng = np.random.default_rng(8000)
+    sizes = [8000, 3]
+    Xs, zs = [], []
+    for n in sizes:
+        xy = rng.uniform(-3e5, 3e5, (n, 2))
+        t = rng.integers(18322, 18331, n).astype(np.float64)
+        X = np.column_stack([xy, t])
+        Xs.append(X)
+        zs.append(0.1 * np.sin(X[:, 0] / 2e5) + 0.05 * np.cos(X[:, 1] / 1.5e5) + rng.normal(0, 0.05, n))
+    cs = np.array([50_000.0, 50_000.0, 1.0])
+    off, Xc, zc = _pack(Xs, zs)
+    theta = np.array([[3.0, 2.5, 4.0, 0.012, 0.004], [1.0, 1.0, 1.0, 1.0, 0.5]])
+    b = eng.make_batch(off, Xc, zc, coords_scale=cs)
+    f, g = eng.eval(b, theta, grad=True)
+    f, g = f.cpu().numpy(), g.cpu().numpy()
+    fr = -gpr.lml(Xs[0] / cs, zs[0], theta[0, :3], theta[0, 3], theta[0, 4])
+    assert abs(f[0] - fr) <= RTOL_FIXED * abs(fr), (f[0], fr)
+    fr1, gr1 = gpr.neg_lml_and_grad(Xs[1] / cs, zs[1], theta[1, :3], theta[1, 3], theta[1, 4])
+    assert abs(f[1] - fr1) <= RTOL_FIXED * abs(fr1)
+    np.testing.assert_allclose(g[1], gr1, rtol=1e-7, atol=1e-12)
+    # gradient of the big expert vs central differences of the CUDA objective (each a full factorisation)
+    for k in (0, 3, 4):
+        h = 1e-5 * theta[0, k]
+        tp, tm = theta.copy(), theta.copy()
+        tp[0, k] += h
+        tm[0, k] -= h
+        fp = eng.eval(b, tp, grad=False)[0].cpu().numpy()[0]
+        fm_ = eng.eval(b, tm, grad=False)[0].cpu().numpy()[0]
+        fd = (fp - fm_) / (2 * h)
+        assert abs(fd - g[0, k]) <= 1e-5 * max(1.0, abs(g[0, k])), (k, fd, g[0, k])
+    P = 96
+    Xp = np.column_stack([rng.uniform(-2e5, 2e5, (P, 2)), np.full(P, 18326.0)])
+    fmean, fvar, _, _ = eng.predict(b, theta, np.array([0, P, P]), Xp)
+    m, v, _ = gpr.predict(Xs[0] / cs, zs[0], Xp / cs, theta[0, :3], theta[0, 3], theta[0, 4])
+    np.testing.assert_allclose(fmean.cpu().numpy(), m, rtol=1e-7, atol=1e-10)
+    np.testing.assert_allclose(fvar.cpu().numpy(), v, rtol=1e-6, atol=1e-10)
+
+
 def test_non_positive_definite_is_reported_not_fatal(eng):
     """The reference aborts the whole run on a failed Cholesky (uncaught TF exception); here the expert gets
     f = +inf, the others are unaffected, and an optimisation started next to such a point still terminates."""
