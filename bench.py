@@ -27,7 +27,14 @@ if ROOT not in sys.path:
 
 # per-launch DRAM traffic (bytes) of the dominant kernel of each phase, from the committed ncu --set full captures
 # (profiles/*_summary.md); filled in when a capture of the current kernel generation exists
-TRAFFIC = {}
+TRAFFIC = {
+    # k_potrf_panel, middle panel (J = 6 of 15, 1773 CTAs, 197 slots, N ~ 1.9k), profiles/r01d_busy.md:
+    # 1437 MB per launch; the algorithmic bytes of that launch (L row and column panels read once per CTA, K tiles
+    # read, L tiles written) are 1.8 GB, i.e. L2 already absorbs part of the operand re-reads
+    "potrf": 1.437e9,
+    "trtri": 2.595e9,     # k_trtri_pass1, level h = 8 (64 x 197 CTAs)
+    "lauum": 3.996e9,     # k_lauum2 (120 x 197 CTAs)
+}
 
 METRIC = "experts/sec (optimise+predict)"
 UNIT = "experts/s"
