@@ -15,6 +15,7 @@
 #include "microbench.cuh"
 #include "sgpr.cuh"
 #include "postproc.cuh"
+#include "preproc.cuh"
 
 using namespace gpsat;
 
@@ -1023,6 +1024,26 @@ extern "C" int gpsat_weighted_groups(const double* ref_dev, const double* to_dev
   k_weighted_groups<<<(unsigned)n_groups, 256, 0, (cudaStream_t)stream>>>(
       ref_dev, to_dev, nd, vals_dev, (long)n, ncol, order_dev, group_off_dev, lengthscale * lengthscale,
       (long)n_groups, out_dev);
+  CK(cudaGetLastError());
+  return 0;
+}
+
+// ---- upstream binning ----
+extern "C" int gpsat_bin_accumulate(const double* x_dev, const double* y_dev, const double* vals_dev,
+                                    const int* group_dev, long long n, const double* x_edges_dev, int n_x_edges,
+                                    double x_round_scale, int x_round_div, const double* y_edges_dev, int n_y_edges,
+                                    double y_round_scale, int y_round_div, int n_groups, double* sum_dev,
+                                    unsigned long long* count_dev, void* stream) {
+  if (!x_dev || !vals_dev || !x_edges_dev || n_x_edges < 2 || !sum_dev || !count_dev || n_groups < 1 ||
+      (y_dev && (!y_edges_dev || n_y_edges < 2)))
+    return fail(GPSAT_EINVAL, "bad argument");
+  if (n <= 0) return 0;
+  BinAxis ax{x_edges_dev, n_x_edges, x_round_scale, x_round_div};
+  BinAxis ay{y_edges_dev, n_y_edges, y_round_scale, y_round_div};
+  const long long want = (n + 255) / 256;
+  const unsigned grid = (unsigned)std::min<long long>(want, 148LL * 16);
+  k_bin_accumulate<<<grid, 256, 0, (cudaStream_t)stream>>>(x_dev, y_dev, vals_dev, group_dev, n, ax, ay, y_dev != nullptr,
+                                                         sum_dev, count_dev);
   CK(cudaGetLastError());
   return 0;
 }

@@ -409,7 +409,17 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_potrf_panel(SlotCtx c, int J, i
   if (I != J) {
     // ---- off-diagonal supertile: L_I,panel = C X_JJ' ----
     if (threadIdx.x == 0) {
-      while (ld_acquire_gpu(c.pflag + s) != J + 1) __nanosleep(200);
+      // Blocks are dispatched in index order, so the slot's diagonal CTA (index < S) is resident or finished by
+      // the time this one runs and the wait is short.  It is bounded anyway (~1 s): a lost flag marks the slot
+      // as failed (objective = +inf) instead of hanging the device.
+      int spins = 0;
+      while (ld_acquire_gpu(c.pflag + s) != J + 1) {
+        __nanosleep(200);
+        if (++spins > 4000000) {
+          c.fail[s] = 1;
+          break;
+        }
+      }
       fence_proxy_async_all();
       if (!xe_issued) {
         mbar_expect_tx(xbar, TILE_BYTES);

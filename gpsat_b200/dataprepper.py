@@ -1,0 +1,165 @@
+"""Upstream binning on the GPU: mirror of ``GPSat.dataprepper.DataPrep``.
+
+  DataPrep.bin_data      GPSat/dataprepper.py:230-407  (scipy.stats.binned_statistic_2d / binned_statistic)
+  DataPrep.bin_data_by   GPSat/dataprepper.py:23-228   (one bin_data per unique by_cols combination; here every
+                                                       group goes through ONE kernel launch)
+
+Statistics computed on the device: "mean", "sum", "count" (csrc/preproc.cuh through gpsat_bin_accumulate); other
+scipy statistics are rejected.  The reference returns an xarray Dataset from bin_data_by; xarray is not a dependency
+here, so bin_data_by returns the frame ``Dataset.to_dataframe()`` would give (``return_df=True`` in the reference):
+a full (y, x, *by_cols) MultiIndex product, sorted, NaN where a bin is empty.  No CPU fallback.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+import pandas as pd
+import torch
+
+from . import _lib
+
+_STATS = ("mean", "sum", "count")
+
+
+def _round_rule(edges):
+    """scipy _bin_numbers: decimal = int(-log10(min edge step)) + 6 -> (scale, divide?)"""
+    dmin = np.diff(edges).min()
+    if dmin == 0:
+        raise ValueError("The smallest edge difference is numerically 0.")
+    decimal = int(-np.log10(dmin)) + 6
+    return (10.0 ** abs(decimal), 1 if decimal < 0 else 0)
+
+
+def _edges(x_range, y_range, grid_res, bin_2d):
+    if x_range is None:
+        x_range = [-4500000.0, 4500000.0]
+        print(f"x_range, not provided, using default: {x_range}")
+    assert x_range[0] < x_range[1], f"x_range should be (min, max), got: {x_range}"
+    if y_range is None:
+        y_range = [-4500000.0, 4500000.0]
+        if bin_2d:
+            print(f"y_range, not provided, using default: {y_range}")
+    assert y_range[0] < y_range[1], f"y_range should be (min, max), got: {y_range}"
+    assert len(x_range) == 2, f"x_range expected to be len = 2, got: {len(x_range)}"
+    assert len(y_range) == 2, f"y_range expected to be len = 2, got: {len(y_range)}"
+    n_x = int(((x_range[1] - x_range[0]) / grid_res) + 1)
+    n_y = int(((y_range[1] - y_range[0]) / grid_res) + 1)
+    return np.linspace(x_range[0], x_range[1], n_x), np.linspace(y_range[0], y_range[1], n_y)
+
+
+def _accumulate(x, y, vals, group, n_groups, x_edge, y_edge, device=0):
+    """-> (sum [G, nx, ny], count [G, nx, ny]) as numpy arrays (ny = 1 for 1-D binning)."""
+    if not torch.cuda.is_available():
+        raise RuntimeError("gpsat_b200.dataprepper needs a CUDA device (there is no CPU fallback)")
+    lib = _lib.load()
+    dev = torch.device("cuda", device)
+    for a, nm in ((x, "x"), (y, "y")):
+        if a is not None and not np.all(np.isfinite(a)):
+            raise ValueError(f"{nm} contains non-finite values.")      # scipy raises the same way
+    up = lambda a, dt: None if a is None else torch.from_numpy(np.ascontiguousarray(a, dtype=dt)).to(dev)
+    xd, yd, vd, gd = up(x, np.float64), up(y, np.float64), up(vals, np.float64), up(group, np.int32)
+    xe, ye = up(x_edge, np.float64), up(y_edge, np.float64)
+    nx, ny = len(x_edge) - 1, (len(y_edge) - 1 if y is not None else 1)
+    s = torch.zeros((n_groups, nx, ny), dtype=torch.float64, device=dev)
+    c = torch.zeros((n_groups, nx, ny), dtype=torch.int64, device=dev)
+    xs, xdv = _round_rule(x_edge)
+    ys, ydv = _round_rule(y_edge) if y is not None else (1.0, 0)
+    ptr = lambda t: None if t is None else C.c_void_p(t.data_ptr())
+    _lib.check(lib.gpsat_bin_accumulate(ptr(xd), ptr(yd), ptr(vd), ptr(gd), len(x), ptr(xe), len(x_edge), xs, xdv,
+                                        ptr(ye) if y is not None else None, len(y_edge) if y is not None else 0,
+                                        ys, ydv, n_groups, ptr(s), ptr(c),
+                                        C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)))
+    return s.cpu().numpy(), c.cpu().numpy()
+
+
+def _statistic(s, c, stat):
+    if stat == "count":
+        return c.astype(np.float64)
+    if stat == "sum":
+        return s
+    with np.errstate(invalid="ignore", divide="ignore"):
+        return np.where(c > 0, s / np.where(c > 0, c, 1), np.nan)
+
+
+class DataPrep:
+    @staticmethod
+    def bin_data(df, x_range=None, y_range=None, grid_res=None, x_col="x", y_col="y", val_col=None,
+                 bin_statistic="mean", bin_2d=True, return_bin_center=True, device=0):
+        """dataprepper.py:230-407: -> (binned [n_y - 1, n_x - 1] (2-D) or [n_x - 1], bin centres / edges)."""
+        assert val_col is not None, "val_col - the column containing values to bin cannot be None"
+        assert grid_res is not None, "grid_res is None, must be supplied - expressed in km"
+        assert len(df) > 0, "dataframe (df) provide must have len > 0"
+        if bin_statistic not in _STATS:
+            raise NotImplementedError(f"bin_statistic: {bin_statistic!r} is not implemented on the device "
+                                      f"(available: {_STATS})")
+        if not bin_2d:
+            y_col = x_col
+        x_edge, y_edge = _edges(x_range, y_range, grid_res, bin_2d)
+        assert x_col in df, f"x_col: {x_col} is not in df columns: {df.columns}"
+        assert y_col in df, f"y_col: {y_col} is not in df columns: {df.columns}"
+        assert val_col in df, f"val_col: {val_col} is not in df columns: {df.columns}"
+        s, c = _accumulate(df[x_col].values, df[y_col].values if bin_2d else None, df[val_col].values, None, 1,
+                           x_edge, y_edge, device)
+        b = _statistic(s[0], c[0], bin_statistic)
+        xy_out = (x_edge, y_edge)
+        if return_bin_center:
+            xy_out = (x_edge[:-1] + np.diff(x_edge) / 2, y_edge[:-1] + np.diff(y_edge) / 2)
+        if bin_2d:
+            return b.T, (xy_out[0], xy_out[1])
+        return b[:, 0].T, xy_out[0]
+
+    @classmethod
+    def bin_data_by(cls, df, col_funcs=None, row_select=None, by_cols=None, val_col=None, x_col="x", y_col="y",
+                    x_range=None, y_range=None, grid_res=None, bin_statistic="mean", bin_2d=True, limit=10000,
+                    return_df=True, verbose=False, device=0):
+        """dataprepper.py:23-228 with ``return_df=True`` semantics (see the module docstring).  ``col_funcs`` /
+        ``row_select`` are applied by the caller (they are the reference's generic frame utilities)."""
+        assert col_funcs is None and row_select is None, "apply col_funcs / row_select before calling bin_data_by"
+        assert return_df, "xarray output is not available: use return_df=True"
+        if bin_2d is False:
+            y_col = x_col
+        assert by_cols is not None, "by_col needs to be provided"
+        if isinstance(by_cols, str):
+            by_cols = [by_cols]
+        assert isinstance(by_cols, (list, tuple)), f"by_cols must be list or tuple, got type: {type(by_cols)}"
+        by_cols = list(by_cols)
+        for bc in by_cols:
+            assert bc in df, f"by_cols value: {bc} is not in df.columns: {df.columns}"
+        assert val_col in df, f"val_col: {val_col} is not in df.columns: {df.columns}"
+        assert x_col in df, f"x_col: {x_col} is not in df.columns: {df.columns}"
+        assert y_col in df, f"y_col: {y_col} is not in df.columns: {df.columns}"
+        assert grid_res is not None, "grid_res is None, must be supplied - expressed in km"
+        stats = bin_statistic if isinstance(bin_statistic, list) else [bin_statistic]
+        for st in stats:
+            if st not in _STATS:
+                raise NotImplementedError(f"bin_statistic: {st!r} is not implemented on the device")
+        # every coordinate of the output is the sorted set of its unique values (xr.combine_by_coords)
+        codes, uniques = [], []
+        for bc in by_cols:
+            cde, unq = pd.factorize(df[bc], sort=True)
+            codes.append(cde)
+            uniques.append(np.asarray(unq))
+        bc_pair = df.loc[:, by_cols].drop_duplicates()
+        assert len(bc_pair) < limit, f"number unique values of by_cols found in data: {len(bc_pair)} > limit: " \
+                                     f"{limit} are you sure you want this many? if so increase limit"
+        shape = [len(u) for u in uniques]
+        group = np.ravel_multi_index(codes, shape).astype(np.int32) if len(by_cols) else np.zeros(len(df), np.int32)
+        G = int(np.prod(shape))
+        x_edge, y_edge = _edges(x_range, y_range, grid_res, bin_2d)
+        s, c = _accumulate(df[x_col].values, df[y_col].values if bin_2d else None, df[val_col].values, group, G,
+                           x_edge, y_edge, device)
+        xc, yc = x_edge[:-1] + np.diff(x_edge) / 2, y_edge[:-1] + np.diff(y_edge) / 2
+        present = np.zeros(G, dtype=bool)
+        present[np.unique(group)] = True            # combinations absent from the data stay NaN for every statistic
+        out = {}
+        for st in stats:
+            b = _statistic(s, c, st)                # [G, nx, ny]
+            b = np.where(present[:, None, None], b, np.nan)
+            b = np.moveaxis(b.reshape(shape + [b.shape[1], b.shape[2]]), [-1, -2], [0, 1])    # [ny, nx, *by]
+            if not bin_2d:
+                b = b[0]
+            out[val_col if len(stats) == 1 else f"{val_col}_{st}"] = b.reshape(-1)
+        levels = ([yc, xc] if bin_2d else [xc]) + uniques
+        names = ([y_col, x_col] if bin_2d else [x_col]) + by_cols
+        return pd.DataFrame(out, index=pd.MultiIndex.from_product(levels, names=names))

@@ -234,6 +234,18 @@ int gpsat_weighted_groups(const double* ref_dev, const double* to_dev, int nd, c
                           int ncol, const long long* order_dev, const long long* group_off_dev,
                           long long n_groups, double lengthscale, double* out_dev, void* stream);
 
+/* Upstream binning: replaces scipy.stats.binned_statistic_2d as called by DataPrep.bin_data
+ * (GPSat/dataprepper.py:230-407) for every by_cols group of DataPrep.bin_data_by (dataprepper.py:23-228) in one launch.
+ * Bin numbers follow scipy: searchsorted(edges, v, side="right"), a value that rounds onto the last edge
+ * (around(v, decimal), decimal = int(-log10(min edge step)) + 6: round_scale = 10^|decimal|, round_div = decimal < 0)
+ * belongs to the last bin; out-of-range rows are dropped.  y_dev = NULL: 1-D binning.  sum_dev (fp64) and count_dev
+ * (uint64), both [n_groups][n_x_edges - 1][n_y_edges - 1] and zeroed by the caller, receive the per-bin sum of vals
+ * and the number of rows; group_dev (int32, NULL = one group) is the row's group. */
+int gpsat_bin_accumulate(const double* x_dev, const double* y_dev, const double* vals_dev, const int* group_dev,
+                         long long n, const double* x_edges_dev, int n_x_edges, double x_round_scale, int x_round_div,
+                         const double* y_edges_dev, int n_y_edges, double y_round_scale, int y_round_div,
+                         int n_groups, double* sum_dev, unsigned long long* count_dev, void* stream);
+
 /* roofline denominator for the factorisation kernels: FP64 mma.sync (DMMA m8n8k4) issue rate of
  * this GPU measured with register-resident accumulator chains (no memory traffic). */
 int gpsat_dmma_peak(int device, int iters, double* tflops_out, double* ms_out);
