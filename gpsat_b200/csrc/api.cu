@@ -305,7 +305,12 @@ static int run_round_flags(gpsat_handle* h, const SlotCtx& c, int nbm, int flags
   const int nsr = (nbm + 1) / 2, ntm = nbm * (nbm + 1) / 2;
   if (prof) { cudaEventRecord(next_event(h), st); h->ev_flops.push_back(flops_third); }
   if (flags & RR_BUILD) {
-    k_build<<<dim3(ntm, c.S), 256, 0, st>>>(c);
+    switch (c.kid) {     // kernel family resolved at compile time inside the elementwise kernels
+      case K_RBF: k_build<K_RBF><<<dim3(ntm, c.S), 256, 0, st>>>(c); break;
+      case K_MATERN32: k_build<K_MATERN32><<<dim3(ntm, c.S), 256, 0, st>>>(c); break;
+      case K_MATERN52: k_build<K_MATERN52><<<dim3(ntm, c.S), 256, 0, st>>>(c); break;
+      default: k_build<K_MATERN12><<<dim3(ntm, c.S), 256, 0, st>>>(c); break;
+    }
     ++h->launches;
   }
   if (prof) cudaEventRecord(next_event(h), st);
@@ -331,7 +336,12 @@ static int run_round_flags(gpsat_handle* h, const SlotCtx& c, int nbm, int flags
   }
   if (prof) cudaEventRecord(next_event(h), st);
   if (flags & RR_TRACE) {
-    k_grad_trace<<<dim3(ntm, c.S), 256, 0, st>>>(c);
+    switch (c.kid) {
+      case K_RBF: k_grad_trace<K_RBF><<<dim3(ntm, c.S), 256, 0, st>>>(c); break;
+      case K_MATERN32: k_grad_trace<K_MATERN32><<<dim3(ntm, c.S), 256, 0, st>>>(c); break;
+      case K_MATERN52: k_grad_trace<K_MATERN52><<<dim3(ntm, c.S), 256, 0, st>>>(c); break;
+      default: k_grad_trace<K_MATERN12><<<dim3(ntm, c.S), 256, 0, st>>>(c); break;
+    }
     ++h->launches;
   }
   if (prof) cudaEventRecord(next_event(h), st);
@@ -959,6 +969,12 @@ extern "C" int gpsat_microbench(int device, int which, int param, int nk, double
     if (which == 2) r = time_launch([&] { k_dmma_chain<4><<<grid, 256>>>(iters, buf); }, &ms);
     if (which == 3) r = time_launch([&] { k_dmma_chain<8><<<grid, 256>>>(iters, buf); }, &ms);
     *tflops_out = 2.0 * 256 * nch * (double)iters * 8 * grid / (ms * 1e-3) / 1e12;
+  } else if (which == 40) {   // max relative error of exp_neg (param 0) / sqrt_pos (param 1) vs libdevice
+    CK(cudaMalloc(&buf, 64));
+    CK(cudaMemset(buf, 0, 64));
+    k_elem_accuracy<<<nsm * 8, 256>>>(param, std::max(1, nk), (unsigned long long*)buf);
+    CK(cudaGetLastError());
+    CK(cudaMemcpy(tflops_out, buf, 8, cudaMemcpyDeviceToHost));
   } else if (which == 30) {   // microseconds per 128x128 diagonal block (one CTA per SM, nk repetitions)
     CK(cudaMalloc(&buf, (size_t)nsm * (6 * TILE_BYTES + 64)));
     CK(cudaMemset(buf, 0, (size_t)nsm * (6 * TILE_BYTES + 64)));

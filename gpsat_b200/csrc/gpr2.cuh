@@ -82,6 +82,7 @@ __device__ __forceinline__ void stage_coords(double* dst, const double* coords_s
 // ------------------------------------------------------------------------------------
 // K1: kernel-matrix build.  grid (ntmax, S), 256 threads: thread = (row, 16-column group).
 // ------------------------------------------------------------------------------------
+template <int KID>
 __global__ void __launch_bounds__(256, 4) k_build(SlotCtx c) {
   __shared__ double xi[MAXD * TB], xj[MAXD * TB], yj[TB];
   const int s = blockIdx.y;
@@ -106,6 +107,28 @@ __global__ void __launch_bounds__(256, 4) k_build(SlotCtx c) {
   double xm[MAXD];
 #pragma unroll
   for (int d = 0; d < MAXD; ++d) xm[d] = (d < c.D) ? xi[d * TB + m] : 0.0;
+  if (i < nb - 1 && j < i) {
+    // interior tile: every row and column is an observation and nothing lies on the diagonal -> no per-entry tests
+    // (staged coordinates beyond D are zero on both sides, so all MAXD terms can be summed)
+#pragma unroll
+    for (int cc = 0; cc < 16; cc += 2) {
+      double v[2];
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const int n = c0 + cc + e;
+        double r2 = 0.0;
+#pragma unroll
+        for (int d = 0; d < MAXD; ++d)
+          if (d < c.D) {
+            const double df = xm[d] - xj[d * TB + n];
+            r2 += df * df;
+          }
+        v[e] = kern_value_t<KID>(r2, kvar);
+      }
+      *reinterpret_cast<double2*>(out + swz(m, c0 + cc)) = make_double2(v[0], v[1]);
+    }
+    return;
+  }
 #pragma unroll
   for (int cc = 0; cc < 16; cc += 2) {
     double v[2];
@@ -121,7 +144,7 @@ __global__ void __launch_bounds__(256, 4) k_build(SlotCtx c) {
             const double df = xm[d] - xj[d * TB + n];
             r2 += df * df;
           }
-        val = kern_value(c.kid, r2, kvar);
+        val = kern_value_t<KID>(r2, kvar);
         if (gi == gj) val += nvar;
       } else if (gi == N && gj < N) {
         val = yj[n];
@@ -588,6 +611,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_lauum2(SlotCtx c) {
 
 // gradient contraction per lower tile: reads (X'X)_ij from Kt, alpha from the augmented row of X.
 // grid (ntmax, S), 256 threads: thread = (row, 16-column group)
+template <int KID>
 __global__ void __launch_bounds__(256, 3) k_grad_trace(SlotCtx c) {
   __shared__ double xi[MAXD * TB], xj[MAXD * TB], ai[TB], aj[TB], red[NG * 8];
   const int s = blockIdx.y;
@@ -615,6 +639,7 @@ __global__ void __launch_bounds__(256, 3) k_grad_trace(SlotCtx c) {
   double g[NG];
 #pragma unroll
   for (int k = 0; k < NG; ++k) g[k] = 0.0;
+  const bool interior = (i < nb - 1) && (j < i);   // all rows / columns are observations, nothing on the diagonal
   if (gi < N) {
     double xm[MAXD];
 #pragma unroll
@@ -626,7 +651,7 @@ __global__ void __launch_bounds__(256, 3) k_grad_trace(SlotCtx c) {
 #pragma unroll
       for (int e = 0; e < 2; ++e) {
         const int n = c0 + cc + e, gj = j * TB + n;
-        if (gj < N) {
+        if (interior || gj < N) {
           const double W = (e ? wv.y : wv.x) - am2 * aj[n];
           double r2 = 0.0, d2[MAXD];
 #pragma unroll
@@ -639,12 +664,12 @@ __global__ void __launch_bounds__(256, 3) k_grad_trace(SlotCtx c) {
             }
           }
           double kv, hv;
-          kern_eval(c.kid, r2, kvar, kv, hv);
+          kern_eval_t<KID>(r2, kvar, kv, hv);
           const double wh = W * hv;
 #pragma unroll
           for (int d = 0; d < MAXD; ++d) g[d] += wh * d2[d];
           g[MAXD] += W * kv;
-          if (gi == gj) g[MAXD + 1] += W;
+          if (!interior && gi == gj) g[MAXD + 1] += W;
         }
       }
     }

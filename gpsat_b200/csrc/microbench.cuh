@@ -120,6 +120,30 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_diag_bench(int reps, double* sc
   }
 }
 
+// accuracy of the lean elementary functions against libdevice: max relative error over a sweep (mode 0: exp_neg on
+// u in [0, 745), mode 1: sqrt_pos on [1e-36, 1e12)), encoded in out[0] via atomicMax on the bit pattern
+__global__ void __launch_bounds__(256) k_elem_accuracy(int mode, int per_thread, unsigned long long* out) {
+  const long tid = blockIdx.x * 256L + threadIdx.x, nthreads = gridDim.x * 256L;
+  double worst = 0.0;
+  for (int it = 0; it < per_thread; ++it) {
+    const double frac = (double)(tid * per_thread + it) / (double)(nthreads * per_thread);
+    double got, ref;
+    if (mode == 0) {
+      const double u = 745.0 * frac * frac;          // denser near 0
+      got = exp_neg(u);
+      ref = exp(-u);
+      if (u > 700.0) { ref = 0.0; }
+    } else {
+      const double x = 1e-36 * exp(110.5 * frac);    // 1e-36 .. 1e12
+      got = sqrt_pos(x);
+      ref = sqrt(x);
+    }
+    const double err = (ref == 0.0) ? fabs(got) : fabs(got / ref - 1.0);
+    worst = fmax(worst, err);
+  }
+  atomicMax(out, (unsigned long long)__double_as_longlong(worst));
+}
+
 // 64x64 core (gemm_core.cuh), same modes
 __global__ void __launch_bounds__(NTHREADS, 1) k_gemm1_bench(const double* tiles, long tiles_per_cta, int nk, int mode,
                                                              double* out) {
