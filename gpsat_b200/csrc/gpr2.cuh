@@ -109,8 +109,9 @@ __global__ void __launch_bounds__(256, 4) k_build(SlotCtx c) {
   for (int d = 0; d < MAXD; ++d) xm[d] = (d < c.D) ? xi[d * TB + m] : 0.0;
   if (i < nb - 1 && j < i) {
     // interior tile: every row and column is an observation and nothing lies on the diagonal -> no per-entry tests
-    // (staged coordinates beyond D are zero on both sides, so all MAXD terms can be summed)
-#pragma unroll
+    // (the loop is deliberately not unrolled: the fully unrolled body was 128 KiB of code and the warps
+    //  stalled on instruction fetch -- ncu stalled_no_instruction 4.8 per issue)
+#pragma unroll 1
     for (int cc = 0; cc < 16; cc += 2) {
       double v[2];
 #pragma unroll
@@ -129,7 +130,7 @@ __global__ void __launch_bounds__(256, 4) k_build(SlotCtx c) {
     }
     return;
   }
-#pragma unroll
+#pragma unroll 1
   for (int cc = 0; cc < 16; cc += 2) {
     double v[2];
 #pragma unroll
@@ -612,7 +613,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_lauum2(SlotCtx c) {
 // gradient contraction per lower tile: reads (X'X)_ij from Kt, alpha from the augmented row of X.
 // grid (ntmax, S), 256 threads: thread = (row, 16-column group)
 template <int KID>
-__global__ void __launch_bounds__(256, 3) k_grad_trace(SlotCtx c) {
+__global__ void __launch_bounds__(256, 4) k_grad_trace(SlotCtx c) {
   __shared__ double xi[MAXD * TB], xj[MAXD * TB], ai[TB], aj[TB], red[NG * 8];
   const int s = blockIdx.y;
   if (!c.active[s]) return;
@@ -645,7 +646,7 @@ __global__ void __launch_bounds__(256, 3) k_grad_trace(SlotCtx c) {
 #pragma unroll
     for (int d = 0; d < MAXD; ++d) xm[d] = (d < c.D) ? xi[d * TB + m] : 0.0;
     const double am2 = 2.0 * ai[m];
-#pragma unroll
+#pragma unroll 1
     for (int cc = 0; cc < 16; cc += 2) {
       const double2 wv = *reinterpret_cast<const double2*>(w + swz(m, c0 + cc));
 #pragma unroll
