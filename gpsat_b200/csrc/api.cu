@@ -303,6 +303,7 @@ static int run_round_flags(gpsat_handle* h, const SlotCtx& c, int nbm, int flags
                            double flops_third) {
   const bool prof = h->profiling && (flags & RR_PROFILE);
   const int nsr = (nbm + 1) / 2, ntm = nbm * (nbm + 1) / 2;
+
   if (prof) { cudaEventRecord(next_event(h), st); h->ev_flops.push_back(flops_third); }
   if (flags & RR_BUILD) {
     switch (c.kid) {     // kernel family resolved at compile time inside the elementwise kernels
@@ -969,6 +970,29 @@ extern "C" int gpsat_microbench(int device, int which, int param, int nk, double
     if (which == 2) r = time_launch([&] { k_dmma_chain<4><<<grid, 256>>>(iters, buf); }, &ms);
     if (which == 3) r = time_launch([&] { k_dmma_chain<8><<<grid, 256>>>(iters, buf); }, &ms);
     *tflops_out = 2.0 * 256 * nch * (double)iters * 8 * grid / (ms * 1e-3) / 1e12;
+  } else if (which == 50 || which == 51) {
+    // task streams of nk k-tiles each (param = tasks per CTA): 50 = 128x64 core, two CTAs per SM; 51 = 128x128 core
+    const long tiles_per_cta = 48;
+    const int ctas = (which == 50) ? 2 * nsm : nsm;
+    const size_t bytes = (size_t)ctas * tiles_per_cta * TILE_BYTES;
+    CK(cudaMalloc(&buf, bytes + (size_t)ctas * 4 * TILE_BYTES));
+    CK(cudaMemset(buf, 0, bytes));
+    const int tasks = std::max(1, param);
+    if (which == 50) {
+      auto kern = k_gemm3_bench<false, false>;
+      CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, G3_SMEM_ELEMS * 8));
+      CK(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+      int occ = 0;
+      CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, G3_THREADS, G3_SMEM_ELEMS * 8));
+      if (occ < 2) { cudaFree(buf); return fail(GPSAT_EINVAL, "128x64 core: occupancy " + std::to_string(occ) + " < 2"); }
+      r = time_launch([&] { kern<<<ctas, G3_THREADS, G3_SMEM_ELEMS * 8>>>(buf, tiles_per_cta, nk, tasks, buf + bytes / 8); }, &ms);
+      *tflops_out = 2.0 * 128 * 64 * 64 * (double)nk * tasks * ctas / (ms * 1e-3) / 1e12;
+    } else {
+      auto kern = k_gemm2_tasks_bench<false, false>;
+      CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, G2_SMEM_ELEMS * 8));
+      r = time_launch([&] { kern<<<ctas, NTHREADS, G2_SMEM_ELEMS * 8>>>(buf, tiles_per_cta, nk, tasks, buf + bytes / 8); }, &ms);
+      *tflops_out = 2.0 * 128 * 128 * 64 * (double)nk * tasks * ctas / (ms * 1e-3) / 1e12;
+    }
   } else if (which == 40) {   // max relative error of exp_neg (param 0) / sqrt_pos (param 1) vs libdevice
     CK(cudaMalloc(&buf, 64));
     CK(cudaMemset(buf, 0, 64));

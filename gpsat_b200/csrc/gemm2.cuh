@@ -67,9 +67,9 @@ __device__ __forceinline__ void bulk_half(double* smem_half, const double* gmem_
 }
 
 // acc += op(A_half) * op(B_half) for this warp's 64x32 slab, 32-deep slice resident in shared memory
-template <bool TA, bool TBm>
+template <bool TA, bool TBm, class FRAG>
 __device__ __forceinline__ void mma_half(Acc2& acc, const double* __restrict__ As, const double* __restrict__ Bs,
-                                         const Frag2& f) {
+                                         const FRAG& f) {
   int aoff[8], boff[4];
   const int sq = (f.q & 3) << 2;
 #pragma unroll
@@ -222,7 +222,8 @@ __device__ __forceinline__ void gemm2_pipeline(Acc2& acc, double* smem, G2Pipe& 
 }
 
 // store this warp's 64x32 slab into a swizzled 64x64 tile (global or shared), scaled
-__device__ __forceinline__ void store_acc2(double* __restrict__ tile, const Acc2& acc, const Frag2& f,
+template <class FRAG>
+__device__ __forceinline__ void store_acc2(double* __restrict__ tile, const Acc2& acc, const FRAG& f,
                                            double scale = 1.0) {
 #pragma unroll
   for (int mi = 0; mi < 8; ++mi) {
