@@ -970,6 +970,12 @@ extern "C" int gpsat_microbench(int device, int which, int param, int nk, double
     if (which == 2) r = time_launch([&] { k_dmma_chain<4><<<grid, 256>>>(iters, buf); }, &ms);
     if (which == 3) r = time_launch([&] { k_dmma_chain<8><<<grid, 256>>>(iters, buf); }, &ms);
     *tflops_out = 2.0 * 256 * nch * (double)iters * 8 * grid / (ms * 1e-3) / 1e12;
+  } else if (which == 5 || which == 6) {   // DMMA chains from ONE warp per scheduler (128-thread CTAs, one per SM)
+    CK(cudaMalloc(&buf, 64));
+    const int iters = nk;
+    if (which == 5) r = time_launch([&] { k_dmma_chain<8><<<nsm, 128>>>(iters, buf); }, &ms);
+    else r = time_launch([&] { k_dmma_chain<32><<<nsm, 128>>>(iters, buf); }, &ms);
+    *tflops_out = 2.0 * 256 * (which == 5 ? 8 : 32) * (double)iters * 4 * nsm / (ms * 1e-3) / 1e12;
   } else if (which == 50 || which == 51) {
     // task streams of nk k-tiles each (param = tasks per CTA): 50 = 128x64 core, two CTAs per SM; 51 = 128x128 core
     const long tiles_per_cta = 48;

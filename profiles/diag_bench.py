@@ -16,3 +16,6 @@ for mode, nm in ((0, "exp_neg vs exp(-u), u in [0, 745)"), (1, "sqrt_pos vs sqrt
 for kid, nm in enumerate(("Matern32", "Matern52", "Matern12", "RBF")):
     assert lib.gpsat_microbench(0, 21, kid, 2000, C.byref(v)) == 0
     print(f"kernel eval rate {nm}: {v.value:.1f} G entries/s")
+for which, nm in ((5, "8 chains"), (6, "32 chains")):
+    assert lib.gpsat_microbench(0, which, 0, 20000, C.byref(v)) == 0
+    print(f"DMMA from one warp per scheduler, {nm}: {v.value:.2f} TFLOP/s")
