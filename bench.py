@@ -28,12 +28,13 @@ if ROOT not in sys.path:
 # per-launch DRAM traffic (bytes) of the dominant kernel of each phase, from the committed ncu --set full captures
 # (profiles/*_summary.md); filled in when a capture of the current kernel generation exists
 TRAFFIC = {
-    # k_potrf_panel, middle panel (J = 6 of 15, 1773 CTAs, 197 slots, N ~ 1.9k), profiles/r01d_busy.md:
-    # 1437 MB per launch; the algorithmic bytes of that launch (L row and column panels read once per CTA, K tiles
-    # read, L tiles written) are 1.8 GB, i.e. L2 already absorbs part of the operand re-reads
-    "potrf": 1.437e9,
-    "trtri": 2.595e9,     # k_trtri_pass1, level h = 8 (64 x 197 CTAs)
-    "lauum": 3.996e9,     # k_lauum2 (120 x 197 CTAs)
+    # k_potrf_panel, panel J = 4 of 17 (2561 CTAs, 197 slots, N ~ 2.1k) from the ncu --set full capture
+    # profiles/r01f_summary.md: 1.64 GB read + 0.31 GB written per launch.  Algorithmic bytes of that launch (every
+    # CTA reads its L row panel and the L column panel once, the K tiles once, and writes its L tiles): 2.6 GB, i.e.
+    # L2 already absorbs part of the operand re-reads (26 % sector hit rate)
+    "potrf": 1.951e9,
+    "trtri": 2.595e9,     # k_trtri_pass1, level h = 8 (64 x 197 CTAs), profiles/r01f_busy.md
+    "lauum": 3.995e9,     # k_lauum2 (120 x 197 CTAs), profiles/r01f_busy.md
 }
 
 METRIC = "experts/sec (optimise+predict)"
