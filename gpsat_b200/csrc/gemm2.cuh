@@ -67,9 +67,14 @@ __device__ __forceinline__ void bulk_half(double* smem_half, const double* gmem_
 }
 
 // acc += op(A_half) * op(B_half) for this warp's 64x32 slab, 32-deep slice resident in shared memory
-template <bool TA, bool TBm, class FRAG>
-__device__ __forceinline__ void mma_half(Acc2& acc, const double* __restrict__ As, const double* __restrict__ Bs,
-                                         const FRAG& f) {
+struct NoHook {
+  __device__ __forceinline__ void operator()() const {}
+};
+// `last_loads_done()` is invoked once, after the fragments of the LAST k-step have arrived in registers (this warp will
+// not read the slice again) and before that step's 32 DMMAs are issued: the ring uses it to release the slot early.
+template <bool TA, bool TBm, class FRAG, class HOOK>
+__device__ __forceinline__ void mma_half_h(Acc2& acc, const double* __restrict__ As, const double* __restrict__ Bs,
+                                           const FRAG& f, HOOK last_loads_done) {
   int aoff[8], boff[4];
   const int sq = (f.q & 3) << 2;
 #pragma unroll
@@ -97,11 +102,31 @@ __device__ __forceinline__ void mma_half(Acc2& acc, const double* __restrict__ A
 #pragma unroll
       for (int ni = 0; ni < 4; ++ni) b[nxt][ni] = Bs[boff[ni] + (TBm ? kk * 32 : (kk ^ sq))];
     }
+    if (ks == 7) {
+      // last step: eight DMMAs that between them read every fragment register first -- once they have issued, the
+      // scoreboard guarantees that all of this warp's shared-memory loads of the slice have returned -- then the
+      // hook, then the remaining 24 DMMAs (which hide whatever latency the hook started)
 #pragma unroll
-    for (int mi = 0; mi < 8; ++mi)
+      for (int mi = 0; mi < 8; ++mi)
+        dmma884(acc.c[mi][mi & 3][0], acc.c[mi][mi & 3][1], a[cur][mi], b[cur][mi & 3]);
+      last_loads_done();
 #pragma unroll
-      for (int ni = 0; ni < 4; ++ni) dmma884(acc.c[mi][ni][0], acc.c[mi][ni][1], a[cur][mi], b[cur][ni]);
+      for (int mi = 0; mi < 8; ++mi)
+#pragma unroll
+        for (int ni = 0; ni < 4; ++ni)
+          if (ni != (mi & 3)) dmma884(acc.c[mi][ni][0], acc.c[mi][ni][1], a[cur][mi], b[cur][ni]);
+    } else {
+#pragma unroll
+      for (int mi = 0; mi < 8; ++mi)
+#pragma unroll
+        for (int ni = 0; ni < 4; ++ni) dmma884(acc.c[mi][ni][0], acc.c[mi][ni][1], a[cur][mi], b[cur][ni]);
+    }
   }
+}
+template <bool TA, bool TBm, class FRAG>
+__device__ __forceinline__ void mma_half(Acc2& acc, const double* __restrict__ As, const double* __restrict__ Bs,
+                                         const FRAG& f) {
+  mma_half_h<TA, TBm>(acc, As, Bs, f, NoHook());
 }
 
 // Ring state of one CTA: mbarriers in shared memory + the number of slices that went through the ring so far
@@ -186,21 +211,23 @@ __device__ __forceinline__ void gemm2_pipeline_t(Acc2& acc, double* smem, G2Pipe
     const uint32_t n = p.count + sl;
     p.wait(n);               // the slice has landed
     const int k = kbeg + (sl >> 1);
+    const bool refill = sl + G2_STAGES < ntot;
+    int* cnt = p.done + p.stage(n);
+    int seen = -1;                      // lane 0: the slot counter before this warp's release
     if (a_of(k, f.ta) != nullptr && b_of(k, f.tb) != nullptr) {
       const double* st = smem + p.stage(n) * G2_STAGE_ELEMS;
-      mma_half<TA, TBm>(acc, st + f.ta * HALF_ELEMS, st + (2 + f.tb) * HALF_ELEMS, f);
+      // the slot is released from inside the last k-step (its operands are in registers by then), so the latency of
+      // the shared-memory atomic hides behind that step's 32 DMMAs instead of idling the pipe at the slice boundary
+      mma_half_h<TA, TBm>(acc, st + f.ta * HALF_ELEMS, st + (2 + f.tb) * HALF_ELEMS, f, [&]() {
+        if (refill && f.lane == 0) seen = atomicAdd(cnt, 1);
+      });
+    } else if (refill && f.lane == 0) {
+      seen = atomicAdd(cnt, 1);
     }
-    if (sl + G2_STAGES < ntot) {
-      // this warp's fragment loads of the slice have all returned (the DMMAs consumed them)
-      __syncwarp();
-      if (f.lane == 0) {
-        int* cnt = p.done + p.stage(n);
-        if (atomicAdd(cnt, 1) == NTHREADS / 32 - 1) {   // last warp out refills the slot
-          atomicExch(cnt, 0);
-          __threadfence_block();
-          issue(sl + G2_STAGES);
-        }
-      }
+    if (seen == NTHREADS / 32 - 1) {    // last warp out refills the slot
+      atomicExch(cnt, 0);
+      __threadfence_block();
+      issue(sl + G2_STAGES);
     }
   }
   if (TAIL) {
