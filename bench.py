@@ -49,7 +49,8 @@ def parse():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="c3", choices=["c3", "c1", "c4", "c5", "tiny"])
     ap.add_argument("--experts-per-step", type=int, default=1024, help="experts per rank per step")
-    ap.add_argument("--cpu-sample", type=int, default=1, help="experts timed by the cpu_baseline leg")
+    ap.add_argument("--cpu-sample", type=int, default=3,
+                    help="experts timed by the cpu_baseline leg / per step of --impl reference (~6 s each)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()
 
