@@ -47,7 +47,7 @@ def parse():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="c3", choices=["c3", "c1", "c4", "c5", "tiny"])
+    ap.add_argument("--workload", default="c3", choices=["c3", "c1", "c2", "c4", "c5", "tiny"])
     ap.add_argument("--experts-per-step", type=int, default=1024, help="experts per rank per step")
     ap.add_argument("--cpu-sample", type=int, default=3,
                     help="experts timed by the cpu_baseline leg / per step of --impl reference (~6 s each)")
@@ -200,9 +200,18 @@ def run_b200(args):
     # does not depend on which part of the (density-varying) domain a rank happens to get
     experts_perm = w["experts"][np.random.default_rng(12345).permutation(E_all)]
 
+    perm = np.random.default_rng(12345).permutation(E_all)
+    theta_all = w.get("theta")          # predict-only workloads: per-expert hyper-parameters to load
+
     def chunk(step):
         c = (step * world + rank) % n_chunks
         return np.ascontiguousarray(experts_perm[c * B:(c + 1) * B])
+
+    def chunk_theta(step):
+        if theta_all is None:
+            return None
+        c = (step * world + rank) % n_chunks
+        return np.ascontiguousarray(theta_all[perm[c * B:(c + 1) * B]])
 
     table_h = torch.from_numpy(w["table"]).pin_memory()
     pred_h = torch.from_numpy(w["pred"]).pin_memory()
@@ -213,7 +222,7 @@ def run_b200(args):
 
     def step_device(step):
         refs = torch.from_numpy(chunk(step)).to(dev)
-        return run_experts(eng, spec, table_d, refs_dev=refs, pred_table_dev=pred_d, **kw)
+        return run_experts(eng, spec, table_d, refs_dev=refs, pred_table_dev=pred_d, theta_init=chunk_theta(step), **kw)
 
     def barrier():
         if world > 1:
@@ -287,13 +296,14 @@ def run_b200(args):
 
     # ---- end to end through the host-buffer API ----
     refs_h = [torch.from_numpy(chunk(args.warmup + args.steps + s)).pin_memory() for s in range(args.steps)]
-    run_experts_host(eng, spec, table_h, experts=refs_h[0], pred_table=pred_h, **kw)
+    th_h = [chunk_theta(args.warmup + args.steps + s) for s in range(args.steps)]
+    run_experts_host(eng, spec, table_h, experts=refs_h[0], pred_table=pred_h, theta_init=th_h[0], **kw)
     barrier()
     t0 = time.perf_counter()
     ev0.record()
     n_e2e, d2h = 0, 0
     for s in range(args.steps):
-        r = run_experts_host(eng, spec, table_h, experts=refs_h[s], pred_table=pred_h, **kw)
+        r = run_experts_host(eng, spec, table_h, experts=refs_h[s], pred_table=pred_h, theta_init=th_h[s], **kw)
         n_e2e += r["n_valid"]
         d2h = sum(v.nbytes for v in r.values() if isinstance(v, np.ndarray))
     ev1.record()

@@ -106,6 +106,23 @@ def workload(name="c3", n_experts=None, seed=SEED):
                     optimise=True,
                     describe="inline_example shape: 200 km expert lattice, ~400-600 obs per expert, "
                              "optimise + predict on the 5 km grid within 200 km")
+    if name == "c2":
+        # configs/example_local_expert_oi.json shape: 363 expert locations (the reference's
+        # example_expert_locations_arctic_no_date.csv has 363 rows), N ~ 400-600, fixed per-expert (smoothed)
+        # hyper-parameters loaded instead of optimised, prediction on the 5 km grid within 200 km (P ~ 5027)
+        E = 363 if n_experts is None else n_experts
+        table = observations(rng, radius_cells=40, days=range(18316, 18337), density_lo=0.14, density_hi=0.22)
+        experts = expert_lattice(E, spacing=200_000.0)
+        half = float(np.abs(experts[:, :2]).max()) + 200_000.0
+        # KAT-5-like ranges of the smoothed tables: l ~ (5, 3, 9), kernel variance ~ 0.015, noise ~ 0.003
+        theta = np.column_stack([rng.uniform(3.0, 8.0, E), rng.uniform(2.0, 6.0, E), rng.uniform(5.0, 9.0, E),
+                                 rng.uniform(0.008, 0.03, E), rng.uniform(0.002, 0.006, E)])
+        return dict(name="c2", table=table, table_cols=["x", "y", "t", "obs"], experts=experts,
+                    expert_cols=["x", "y", "t"], pred=pred_grid(half), pred_cols=["x", "y"], max_dist=200_000.0,
+                    local_select=LOCAL_SELECT, model=MODEL_C1, coords_col=["x", "y", "t"], obs_col="obs",
+                    optimise=False, theta=theta,
+                    describe="example_local_expert_oi.json shape: 363 experts, ~400-600 obs per expert, fixed "
+                             "(loaded) hyper-parameters, predict-only on the 5 km grid within 200 km (P ~ 5027)")
     if name == "c4":
         # 5 km-resolution expert grid (the full run has ~1e5 experts; a step takes a lattice sample of them), dense
         # along-track observations: variable N up to ~8k per expert, full optimisation
