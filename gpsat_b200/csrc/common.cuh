@@ -28,7 +28,7 @@ constexpr int TILE_ELEMS = TB * TB;    // 4096 doubles
 constexpr int TILE_BYTES = TILE_ELEMS * 8;
 constexpr int MAXD = 4;                // max coordinate dimension
 constexpr int MAXP = MAXD + 2;         // lengthscales..., kernel variance, likelihood variance
-constexpr int NTHREADS = 256;          // CTA size of the tile kernels (8 warps: 4 (M) x 2 (N))
+constexpr int NTHREADS = 256;          // CTA size of the tile kernels (8 warps, two per scheduler)
 
 enum KernelId { K_MATERN32 = 0, K_MATERN52 = 1, K_MATERN12 = 2, K_RBF = 3 };
 
@@ -38,7 +38,7 @@ __host__ __device__ __forceinline__ int swz(int r, int c) {
 }
 __host__ __device__ __forceinline__ long tri_index(int i, int j) { return (long)i * (i + 1) / 2 + j; }
 
-// ---- cp.async (LDGSTS) 16-byte copies ----
+// ---- cp.async (LDGSTS) 16-byte copies (micro-benchmark baseline only; the kernels use the TMA helpers below) ----
 __device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
   uint32_t s = (uint32_t)__cvta_generic_to_shared(smem);
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gmem));

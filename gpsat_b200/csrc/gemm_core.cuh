@@ -2,9 +2,11 @@
 //
 // tcgen05 has no f64 kind, so the FP64 tensor path on sm_100a is warp-level DMMA with
 // register accumulators.  One CTA (8 warps, 4 along M x 2 along N, 16x32 per warp) owns one
-// 64x64 output tile and streams 64x64 operand tiles (32 KiB contiguous blobs, see common.cuh)
-// through a 2-stage cp.async ring in shared memory.  Both operands can be consumed in either
-// orientation straight from the swizzled image:
+// 64x64 output tile.  mma_tile() multiplies two tiles resident in shared memory; the production kernels use it
+// for the 64^3 products inside the diagonal 128x128 blocks (gpr2.cuh: diag_block_128).  gemm_pipeline() -- the
+// original 2-stage per-thread cp.async ring over whole tiles -- is kept only as the baseline of the
+// micro-benchmarks ("core64" lines); everything hot streams through the TMA ring of gemm2.cuh.
+// Both operands can be consumed in either orientation straight from the swizzled image:
 //   TA = false : A[m][k] = Atile(m, k)        TA = true : A[m][k] = Atile(k, m)
 //   TBm = false: B[k][n] = Btile(n, k)  (NT)  TBm = true: B[k][n] = Btile(k, n)
 #pragma once
