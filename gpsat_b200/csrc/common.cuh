@@ -94,6 +94,14 @@ __device__ __forceinline__ void bulk_g2s(void* smem, const void* gmem, uint32_t 
                : "memory");
 }
 
+// ---- 256-bit global accesses (sm_100: LDG.256 / STG.256): one full 32-byte sector per lane and instruction ----
+__device__ __forceinline__ void st_global_v4(double* p, double a, double b, double c, double d) {
+  asm volatile("st.global.v4.f64 [%0], {%1,%2,%3,%4};" ::"l"(p), "d"(a), "d"(b), "d"(c), "d"(d) : "memory");
+}
+__device__ __forceinline__ void ld_global_v4(const double* p, double& a, double& b, double& c, double& d) {
+  asm volatile("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(a), "=d"(b), "=d"(c), "=d"(d) : "l"(p));
+}
+
 // ---- FP64 tensor-core MMA: D(8x8) += A(8x4) * B(4x8) ----
 // A: lane holds A[lane/4][lane%4]; B: lane holds B[lane%4][lane/4]; C: lane holds C[lane/4][2*(lane%4)+{0,1}]
 __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {

@@ -112,10 +112,10 @@ __global__ void __launch_bounds__(256, 4) k_build(SlotCtx c) {
     // (the loop is deliberately not unrolled: the fully unrolled body was 128 KiB of code and the warps
     //  stalled on instruction fetch -- ncu stalled_no_instruction 4.8 per issue)
 #pragma unroll 1
-    for (int cc = 0; cc < 16; cc += 2) {
-      double v[2];
+    for (int cc = 0; cc < 16; cc += 4) {
+      double v[4];
 #pragma unroll
-      for (int e = 0; e < 2; ++e) {
+      for (int e = 0; e < 4; ++e) {
         const int n = c0 + cc + e;
         double r2 = 0.0;
 #pragma unroll
@@ -126,15 +126,15 @@ __global__ void __launch_bounds__(256, 4) k_build(SlotCtx c) {
           }
         v[e] = kern_value_t<KID>(r2, kvar);
       }
-      *reinterpret_cast<double2*>(out + swz(m, c0 + cc)) = make_double2(v[0], v[1]);
+      st_global_v4(out + swz(m, c0 + cc), v[0], v[1], v[2], v[3]);   // 4 consecutive columns = one 32-byte sector
     }
     return;
   }
 #pragma unroll 1
-  for (int cc = 0; cc < 16; cc += 2) {
-    double v[2];
+  for (int cc = 0; cc < 16; cc += 4) {
+    double v[4];
 #pragma unroll
-    for (int e = 0; e < 2; ++e) {
+    for (int e = 0; e < 4; ++e) {
       const int n = c0 + cc + e, gj = j * TB + n;
       double val;
       if (gi < N && gj < N) {
@@ -154,7 +154,7 @@ __global__ void __launch_bounds__(256, 4) k_build(SlotCtx c) {
       }
       v[e] = val;
     }
-    *reinterpret_cast<double2*>(out + swz(m, c0 + cc)) = make_double2(v[0], v[1]);
+    st_global_v4(out + swz(m, c0 + cc), v[0], v[1], v[2], v[3]);
   }
 }
 
@@ -647,13 +647,14 @@ __global__ void __launch_bounds__(256, 4) k_grad_trace(SlotCtx c) {
     for (int d = 0; d < MAXD; ++d) xm[d] = (d < c.D) ? xi[d * TB + m] : 0.0;
     const double am2 = 2.0 * ai[m];
 #pragma unroll 1
-    for (int cc = 0; cc < 16; cc += 2) {
-      const double2 wv = *reinterpret_cast<const double2*>(w + swz(m, c0 + cc));
+    for (int cc = 0; cc < 16; cc += 4) {
+      double wv[4];
+      ld_global_v4(w + swz(m, c0 + cc), wv[0], wv[1], wv[2], wv[3]);
 #pragma unroll
-      for (int e = 0; e < 2; ++e) {
+      for (int e = 0; e < 4; ++e) {
         const int n = c0 + cc + e, gj = j * TB + n;
         if (interior || gj < N) {
-          const double W = (e ? wv.y : wv.x) - am2 * aj[n];
+          const double W = wv[e] - am2 * aj[n];
           double r2 = 0.0, d2[MAXD];
 #pragma unroll
           for (int d = 0; d < MAXD; ++d) {
