@@ -86,12 +86,11 @@ template <int KID>
 __global__ void __launch_bounds__(256, 4) k_build(SlotCtx c) {
   __shared__ double xi[MAXD * TB], xj[MAXD * TB], yj[TB];
   const int s = blockIdx.y;
-  if (!c.active[s]) return;
-  const int nb = c.nb[s];
+  const int act = c.active[s], nb = c.nb[s], N = c.n[s];
+  if (!act) return;
   int i, j;
   tri_decode(blockIdx.x, i, j);
   if (i >= nb) return;
-  const int N = c.n[s];
   const double* th = c.theta + s * MAXP;
   const double* cs = c.coords + (long)s * MAXD * c.npmax;
   stage_coords(xi, cs, c.npmax, c.D, th, i, N);
@@ -374,11 +373,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_potrf_panel(SlotCtx c, int J, i
     s = b / nd;
     I = J + 1 + b % nd;
   }
-  if (!c.active[s]) return;
-  const int nb = c.nb[s];
+  // the three words of slot state are fetched together: one L2 round trip instead of three before the first copy
+  const int act = c.active[s], nb = c.nb[s], N = c.n[s];
+  if (!act) return;
   const int j0 = 2 * J, j1 = 2 * J + 1;
   if (2 * I >= nb) return;
-  const int N = c.n[s];
   double* Lt = c.Lt + (long)s * c.tile_stride;
   double* Kt = c.Kt + (long)s * c.tile_stride;
   double* Xt = c.Xt + (long)s * c.tile_stride;
@@ -398,7 +397,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_potrf_panel(SlotCtx c, int J, i
   double* sXe = smem + G2_SMEM_ELEMS;         // X11 (or X00 when the panel has one tile column) -- outside the ring
   const double* xe_src = two ? tile_ptr(Xt, j1, j1) : tile_ptr(Xt, j0, j0);
   bool xe_issued = false;
-  if (I != J && threadIdx.x == 0 && ld_acquire_gpu(c.pflag + s) == J + 1) {   // already published: the common case
+  // (thread 32 owns the X_JJ fetches, so that thread 0 goes straight to the first ring copies)
+  if (I != J && threadIdx.x == 32 && ld_acquire_gpu(c.pflag + s) == J + 1) {   // already published: the common case
     fence_proxy_async_all();
     mbar_expect_tx(xbar, TILE_BYTES);
     bulk_g2s(sXe, xe_src, TILE_BYTES, xbar);
@@ -432,7 +432,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_potrf_panel(SlotCtx c, int J, i
   __syncthreads();   // every warp has read its K tile: the ring is free
   if (I != J) {
     // ---- off-diagonal supertile: L_I,panel = C X_JJ' ----
-    if (threadIdx.x == 0) {
+    if (threadIdx.x == 32) {
       // Blocks are dispatched in index order, so the slot's diagonal CTA (index < S) is resident or finished by
       // the time this one runs and the wait is short.  It is bounded anyway (~1 s): a lost flag marks the slot
       // as failed (objective = +inf) instead of hanging the device.
@@ -538,8 +538,9 @@ __device__ __forceinline__ bool trtri_decode(int bx, int h, int nsr, int& P, int
 __global__ void __launch_bounds__(NTHREADS, 1) k_trtri_pass1(SlotCtx c, int h) {
   extern __shared__ __align__(128) double smem[];
   const int s = blockIdx.y;
-  if (!c.active[s]) return;
-  const int nb = c.nb[s], nsr = (nb + 1) >> 1;
+  const int act = c.active[s], nb = c.nb[s];
+  if (!act) return;
+  const int nsr = (nb + 1) >> 1;
   int P, Q, mid;
   if (!trtri_decode(blockIdx.x, h, nsr, P, Q, mid)) return;
   double* Lt = c.Lt + (long)s * c.tile_stride;
@@ -560,8 +561,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_trtri_pass1(SlotCtx c, int h) {
 __global__ void __launch_bounds__(NTHREADS, 1) k_trtri_pass2(SlotCtx c, int h) {
   extern __shared__ __align__(128) double smem[];
   const int s = blockIdx.y;
-  if (!c.active[s]) return;
-  const int nb = c.nb[s], nsr = (nb + 1) >> 1;
+  const int act = c.active[s], nb = c.nb[s];
+  if (!act) return;
+  const int nsr = (nb + 1) >> 1;
   int P, Q, mid;
   if (!trtri_decode(blockIdx.x, h, nsr, P, Q, mid)) return;
   double* Lt = c.Lt + (long)s * c.tile_stride;
@@ -586,8 +588,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_trtri_pass2(SlotCtx c, int h) {
 __global__ void __launch_bounds__(NTHREADS, 1) k_lauum2(SlotCtx c) {
   extern __shared__ __align__(128) double smem[];
   const int s = blockIdx.y;
-  if (!c.active[s]) return;
-  const int nb = c.nb[s], nsr = (nb + 1) >> 1;
+  const int act = c.active[s], nb = c.nb[s];
+  if (!act) return;
+  const int nsr = (nb + 1) >> 1;
   int I, J;
   tri_decode(blockIdx.x, I, J);
   if (I >= nsr) return;
@@ -616,12 +619,11 @@ template <int KID>
 __global__ void __launch_bounds__(256, 4) k_grad_trace(SlotCtx c) {
   __shared__ double xi[MAXD * TB], xj[MAXD * TB], ai[TB], aj[TB], red[NG * 8];
   const int s = blockIdx.y;
-  if (!c.active[s]) return;
-  const int nb = c.nb[s];
+  const int act = c.active[s], nb = c.nb[s], N = c.n[s];
+  if (!act) return;
   int i, j;
   tri_decode(blockIdx.x, i, j);
   if (i >= nb) return;
-  const int N = c.n[s];
   const double* th = c.theta + s * MAXP;
   const double* cs = c.coords + (long)s * MAXD * c.npmax;
   stage_coords(xi, cs, c.npmax, c.D, th, i, N);
