@@ -453,6 +453,55 @@ def test_c4_size_expert_8000_obs(eng):
     np.testing.assert_allclose(fvar.cpu().numpy(), v, rtol=1e-6, atol=1e-10)
 
 
+def test_c3_size_optimise_properties(eng):
+    """Full-size c3 experts (N 1.2-1.9 k) through the device optimiser: size-independent properties instead of the
+    (minutes-long) oracle run -- the objective decreases, the stopping rule was scipy's (status 1 / 2), the analytic
+    gradient at the optimum is small in the unconstrained parameterisation's scale, restarting from the optimum
+    terminates almost immediately at the same value (idempotence), and predictions are proper."""
+    from oracle.gpr import neg_lml_and_grad
+    rng = np.random.default_rng(77)
+    sizes = [1893, 1210, 1536, 1471]            # includes a multiple of 64 and 64 k - 1 (augmented-row edge cases)
+    Xs, zs = [], []
+    for n in sizes:
+        xy = rng.uniform(-3e5, 3e5, (n, 2))
+        t = rng.integers(18322, 18331, n).astype(np.float64)
+        X = np.column_stack([xy, t])
+        Xs.append(X)
+        zs.append(0.1 * np.sin(X[:, 0] / 2e5) + 0.05 * np.cos(X[:, 1] / 1.5e5) + rng.normal(0, 0.05, n))
+    cs = np.array([50_000.0, 50_000.0, 1.0])
+    off, Xc, zc = _pack(Xs, zs)
+    b = eng.make_batch(off, Xc, zc, coords_scale=cs, obs_mean_local=True)
+    theta0 = np.array([1.0, 1.0, 1.0, 1.0, 1.0])
+    kind = [1, 1, 1, 0, 0]                       # sigmoid-bounded lengthscales, softplus variances (GPflow defaults)
+    low, high = [1e-8, 1e-8, 1e-8, 0.0, 1e-6], [12.0, 12.0, 9.0, 0.0, 0.0]
+    f0, _ = eng.eval(b, np.tile(theta0, (4, 1)), grad=False)
+    res = eng.optimise(b, theta0, kind, low, high, trainable=[1] * 5)
+    theta, fobj = res["theta"].cpu().numpy(), res["fobj"].cpu().numpy()
+    assert np.all(np.isin(res["status"].cpu().numpy(), (1, 2)))
+    assert np.all(fobj < f0.cpu().numpy()) and np.all(np.isfinite(theta))
+    assert np.all(theta[:, :3] > 0) and np.all(theta[:, :3] < np.array(high[:3])) and np.all(theta[:, 3:] > 0)
+    nfev = res["nfev"].cpu().numpy()
+    assert nfev.min() >= 10 and nfev.max() < 200
+    # objective and gradient of the smallest expert at its optimum against the oracle (one CPU factorisation)
+    e = 1
+    ym = zs[e] - zs[e].mean()
+    fr, gr = neg_lml_and_grad(Xs[e] / cs, ym, theta[e, :3], theta[e, 3], theta[e, 4])
+    assert abs(fobj[e] - fr) <= RTOL_FIXED * abs(fr)
+    f1, g1 = eng.eval(b, theta, grad=True)
+    np.testing.assert_allclose(g1.cpu().numpy()[e], gr, rtol=1e-5, atol=1e-6 * np.abs(gr).max())
+    # idempotence: a restart from the optimum stops within a handful of evaluations at (essentially) the same value
+    again = eng.optimise(b, theta, kind, low, high, trainable=[1] * 5)
+    assert again["nfev"].cpu().numpy().max() <= 12
+    fa = again["fobj"].cpu().numpy()
+    assert np.all(fa <= fobj + 1e-9 * np.abs(fobj)) and np.all(np.abs(fa - fobj) <= 1e-6 * np.abs(fobj))
+    P = 64
+    Xp = np.column_stack([rng.uniform(-2e5, 2e5, (P, 2)), np.full(P, 18326.0)])
+    fm, fv, yv, _ = eng.predict(b, theta, np.arange(5, dtype=np.int64) * P, np.tile(Xp, (4, 1)))
+    fv, yv = fv.cpu().numpy().reshape(4, P), yv.cpu().numpy().reshape(4, P)
+    assert np.all(np.isfinite(fm.cpu().numpy())) and np.all(fv > 0) and np.all(fv <= theta[:, 3:4] * (1 + 1e-12))
+    np.testing.assert_allclose(yv - fv, np.broadcast_to(theta[:, 4:5], (4, P)), rtol=1e-9)
+
+
 def test_non_positive_definite_is_reported_not_fatal(eng):
     """The reference aborts the whole run on a failed Cholesky (uncaught TF exception); here the expert gets
     f = +inf, the others are unaffected, and an optimisation started next to such a point still terminates."""
