@@ -96,6 +96,42 @@ def test_factor_and_inverse(eng, n):
 # ---------------------------------------------------------------------------------------------
 # L1 + G1
 # ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("D", [1, 2, 4])
+def test_randomised_dimensions_kernels_sizes(eng, D):
+    """Differential run over coordinate dimension x kernel x size (incl. the tile-edge sizes) x obs_scale:
+    objective, gradient and prediction against the oracle at the fixed-parameter tolerance."""
+    rng = np.random.default_rng(100 + D)
+    sizes = [1, 2, 3, 63, 64, 65, 127, 128, 129, 191, 192, 193, 257]
+    for kernel in KERNELS:
+        Xs, zs = [], []
+        for n in sizes:
+            X = rng.uniform(0, 6, (n, D))
+            Xs.append(X)
+            zs.append(np.sin(X[:, 0]) + 0.3 * np.cos(1.7 * X[:, -1]) + 0.1 * rng.standard_normal(n))
+        off, Xc, zc = _pack(Xs, zs)
+        E = len(sizes)
+        cs = rng.uniform(0.5, 2.0, D)
+        oscale = 1.7
+        theta = np.column_stack([rng.uniform(0.5, 3.0, (E, D)), rng.uniform(0.2, 2.0, E), rng.uniform(0.01, 0.2, E)])
+        b = eng.make_batch(off, Xc, zc, kernel=kernel, coords_scale=cs, obs_scale=oscale)
+        f, g = eng.eval(b, theta, grad=True)
+        f, g = f.cpu().numpy(), g.cpu().numpy()
+        P = 9
+        Xp = rng.uniform(0, 6, (P, D))
+        fm, fv, yv, _ = eng.predict(b, theta, np.arange(E + 1, dtype=np.int64) * P, np.tile(Xp, (E, 1)))
+        fm, fv = fm.cpu().numpy().reshape(E, P), fv.cpu().numpy().reshape(E, P)
+        for e, n in enumerate(sizes):
+            y = zs[e] / oscale
+            fr, gr = gpr.neg_lml_and_grad(Xs[e] / cs, y, theta[e, :D], theta[e, D], theta[e, D + 1], kernel)
+            assert abs(f[e] - fr) <= RTOL_FIXED * max(abs(fr), 1.0), (kernel, n, f[e], fr)
+            np.testing.assert_allclose(g[e], gr, rtol=1e-7, atol=1e-7 * max(np.abs(gr).max(), 1.0),
+                                       err_msg=f"{kernel} n={n}")
+            m, v, _ = gpr.predict(Xs[e] / cs, y, Xp / cs, theta[e, :D], theta[e, D], theta[e, D + 1], kernel)
+            np.testing.assert_allclose(fm[e], m, rtol=1e-7, atol=1e-9, err_msg=f"{kernel} n={n}")
+            np.testing.assert_allclose(fv[e], v, rtol=1e-6, atol=1e-10, err_msg=f"{kernel} n={n}")
+
+
+
 @pytest.mark.parametrize("kernel", KERNELS)
 def test_objective_and_gradient_ragged_batch(eng, kernel):
     rng = np.random.default_rng(5)
