@@ -94,13 +94,18 @@ def sel_terms(local_select, table_cols, ref_cols):
 
 def run_experts(eng: Engine, spec: ModelSpec, table_dev: torch.Tensor, table_cols, obs_col, coords_col,
                 refs_dev: torch.Tensor, ref_cols, local_select, pred_table_dev=None, pred_cols=None,
-                max_dist=None, optimise=True, predict=True, min_obs=3, theta_init=None):
+                max_dist=None, optimise=True, predict=True, min_obs=3, theta_init=None, count_only=False,
+                inducing_local=None):
     """Run the loop body for every row of refs_dev.  All inputs / outputs are device tensors.
 
     table_dev [ncols, n] (column-major observation table), refs_dev [E, nref] expert rows,
     pred_table_dev [npc, n_pred] (None: predict at the expert location).
     theta_init [E, D+2]: per-expert start values (load_params); constraints' move_within_tol is
     applied to them like the reference does after loading (local_experts.py:1086-1115).
+    count_only: stop after the selection counts and the skip rules (no model work).
+    inducing_local: sparse model only -- per VALID expert (in order) the local row indices of its inducing points,
+    drawn by the caller (the multi-GPU driver draws them for the whole list so that a shard sees the same draws as
+    a single-GPU run); None: drawn here with numpy's global RNG like the reference.
     """
     dev = eng.device
     D = len(coords_col)
@@ -131,7 +136,7 @@ def run_experts(eng: Engine, spec: ModelSpec, table_dev: torch.Tensor, table_col
     out = {"num_obs": ocounts, "has_pred": has_pred, "too_few": too_few, "valid": valid, "valid_idx": vidx}
     Ev = int(vidx.numel())
     out["n_valid"] = Ev
-    if Ev == 0:
+    if Ev == 0 or count_only:
         return out
     refs_v = refs_dev.index_select(0, vidx).contiguous()
     ooff = torch.zeros(Ev + 1, dtype=torch.int64, device=dev)
@@ -161,7 +166,7 @@ def run_experts(eng: Engine, spec: ModelSpec, table_dev: torch.Tensor, table_col
     sparse = spec.num_inducing_points is not None
     sb = None
     if sparse:
-        zoff_h, zidx = inducing_rows(ooff_h, spec.num_inducing_points)
+        zoff_h, zidx = inducing_rows(ooff_h, spec.num_inducing_points, inducing_local)
         zc = coords.index_select(0, torch.as_tensor(zidx, device=dev))
         sb = eng.make_sgpr_batch(batch, zoff_h, zc)
         csd = torch.as_tensor(np.broadcast_to(np.asarray(cs, dtype=np.float64).ravel(), (D,)).copy(), device=dev)
@@ -202,26 +207,35 @@ def run_experts(eng: Engine, spec: ModelSpec, table_dev: torch.Tensor, table_col
     return out
 
 
-def inducing_rows(obs_offsets_host: np.ndarray, num_inducing_points: int):
-    """Row indices (into the concatenated local data) of every expert's inducing points.
+def inducing_local_rows(counts, num_inducing_points: int):
+    """Per expert, the LOCAL row indices (into its own selected observations) of its inducing points.
 
     The reference shuffles a copy of the expert's coordinates with numpy's GLOBAL RNG and keeps the
-    first M rows (all rows when N < M).  Shuffling an index vector consumes exactly the same random
-    draws, so with the same seed and expert order this reproduces the reference's choice.
+    first M rows (all rows when N < M, gpflow_models.py:809-819).  Shuffling an index vector consumes exactly the
+    same random draws, so with the same seed and expert order this reproduces the reference's choice.
     """
-    zoff = [0]
-    idx = []
-    for e in range(len(obs_offsets_host) - 1):
-        o0, n = int(obs_offsets_host[e]), int(obs_offsets_host[e + 1] - obs_offsets_host[e])
+    out = []
+    for n in counts:
+        n = int(n)
         if n < num_inducing_points:
-            sel = np.arange(n, dtype=np.int64)
+            out.append(np.arange(n, dtype=np.int64))
         else:
             perm = np.arange(n, dtype=np.int64)
             np.random.shuffle(perm)
-            sel = perm[:num_inducing_points]
-        idx.append(o0 + sel)
-        zoff.append(zoff[-1] + len(sel))
-    return np.array(zoff, dtype=np.int64), np.concatenate(idx) if idx else np.zeros(0, dtype=np.int64)
+            out.append(perm[:num_inducing_points])
+    return out
+
+
+def inducing_rows(obs_offsets_host: np.ndarray, num_inducing_points: int, local=None):
+    """Row indices (into the concatenated local data) of every expert's inducing points + their CSR offsets."""
+    off = np.asarray(obs_offsets_host, dtype=np.int64)
+    if local is None:
+        local = inducing_local_rows(np.diff(off), num_inducing_points)
+    assert len(local) == len(off) - 1
+    zoff = np.zeros(len(off), dtype=np.int64)
+    zoff[1:] = np.cumsum([len(x) for x in local])
+    idx = [off[e] + np.asarray(x, dtype=np.int64) for e, x in enumerate(local)]
+    return zoff, (np.concatenate(idx) if idx else np.zeros(0, dtype=np.int64))
 
 
 def _move_within_tol(theta: torch.Tensor, spec: ModelSpec, hp: HyperParams) -> torch.Tensor:
@@ -245,7 +259,7 @@ def _move_within_tol(theta: torch.Tensor, spec: ModelSpec, hp: HyperParams) -> t
 
 def run_experts_host(eng: Engine, spec: ModelSpec, table, table_cols, obs_col, coords_col, experts, ref_cols,
                      local_select, pred_table=None, pred_cols=None, max_dist=None, optimise=True, predict=True,
-                     min_obs=3, theta_init=None):
+                     min_obs=3, theta_init=None, count_only=False):
     """Host-buffer entry: numpy / (pinned) CPU tensors in, numpy out.  This is the call the
     LocalExpertOI-compatible driver makes; its cost includes every host<->device copy."""
     dev = eng.device
@@ -253,12 +267,13 @@ def run_experts_host(eng: Engine, spec: ModelSpec, table, table_cols, obs_col, c
     def up(x):
         if x is None:
             return None
-        t = x if isinstance(x, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(x, dtype=np.float64))
+        t = x if isinstance(x, torch.Tensor) else torch.from_numpy(np.require(x, dtype=np.float64,
+                                                                              requirements=["C", "W"]))
         return t.to(dev, non_blocking=True)
 
     res = run_experts(eng, spec, up(table), table_cols, obs_col, coords_col, up(experts), ref_cols, local_select,
                       pred_table_dev=up(pred_table), pred_cols=pred_cols, max_dist=max_dist, optimise=optimise,
-                      predict=predict, min_obs=min_obs, theta_init=theta_init)
+                      predict=predict, min_obs=min_obs, theta_init=theta_init, count_only=count_only)
     out = {}
     for k, v in res.items():
         out[k] = v.cpu().numpy() if isinstance(v, torch.Tensor) else v

@@ -1,34 +1,42 @@
 """LocalExpertOI with a batched dispatch: the reference's orchestrator surface over the CUDA engine.
 
-Mirrors ``GPSat.local_experts.LocalExpertOI`` (local_experts.py:116-1463) for the path BASELINE.json
-names: the constructor takes the same four config dicts, ``run`` takes the same arguments and emits
-the same tables (``run_details``, ``preds``, one table per hyper-parameter, ``expert_locs``,
-``oi_config``), each indexed by the expert's coords_col values (local_experts.py:691-747), in the
-same expert order the sequential loop (local_experts.py:930-1260) would append them.
+Mirrors ``GPSat.local_experts.LocalExpertOI`` (local_experts.py:116-1463) for the path BASELINE.json names: the
+constructor takes the same four config dicts (read through ``gpsat_b200.dataloader``, which restates the slice of
+``DataLoader.load`` the reference uses, so configs/example_local_expert_oi.json is accepted unchanged), ``run`` takes
+the same arguments and appends the same tables to the same HDF5 file with the same ``HDFStore.append`` keyword
+arguments: ``oi_config`` (utils.py:1136-1254), ``expert_locs`` (local_experts.py:882-903), ``run_details``,
+``preds`` and one table per hyper-parameter (local_experts.py:499-550), each indexed by the expert's coords_col
+values (local_experts.py:691-747), rows in the order the sequential loop (local_experts.py:930-1260) appends them.
 
-What is different by design: all experts that share a global ``where`` (local_experts.py:426-472)
-are selected, optimised and predicted in ONE call of the batched engine instead of one Python model
-per expert.  ``load_params={"previous": True}`` (order-dependent EMA warm start,
-local_experts.py:1079-1083,1200-1217) cannot be batched and is rejected.
+What is different by design: consecutive experts are processed in chunks (``max_batch``); inside a chunk all
+experts that share a global ``where`` (local_experts.py:426-472) are selected, optimised and predicted in ONE call of
+the batched engine instead of one Python model per expert, and the chunk's tables are flushed to the store before the
+next chunk starts (the reference flushes every ``store_every`` experts; here a chunk is the flush unit, so a crash
+loses at most one chunk and a restart resumes from ``run_details`` exactly like the reference's,
+local_experts.py:474-497).  ``load_params={"previous": True}`` (order-dependent EMA warm start,
+local_experts.py:1079-1083,1200-1217) and ``replacement_threshold`` (per-expert model switch, :1021-1041) cannot be
+batched and are rejected.
 """
 from __future__ import annotations
 
 import datetime
+import importlib
 import json
 import os
 import re
+import sys
 import time
+import warnings
+from ast import literal_eval
 
 import numpy as np
 import pandas as pd
 
+from . import dataloader as dl
 from .batched import ModelSpec
 from .distributed import run_experts_sharded
 from .model import B200GPRModel, B200SGPRModel, get_model as _get_model
-from .params import PARAM_NAMES
-
-_COMP = {">=": np.greater_equal, ">": np.greater, "==": np.equal, "<": np.less, "<=": np.less_equal,
-         "!=": np.not_equal}
+from .params import HyperParams, PARAM_NAMES
 
 
 def pretty_print_class(x):
@@ -41,65 +49,106 @@ def pretty_print_class(x):
     return out
 
 
-def _load_frame(source, table=None):
-    if isinstance(source, pd.DataFrame):
-        return source
-    assert isinstance(source, str), f"source must be a DataFrame or a file path, got: {type(source)}"
-    ext = os.path.splitext(source)[1].lower()
-    if ext == ".csv":
-        return pd.read_csv(source)
-    if ext in (".parquet", ".pq"):
-        return pd.read_parquet(source)
-    if ext in (".h5", ".hdf5"):
-        return pd.read_hdf(source, key=table)      # needs PyTables, like the reference
-    if ext in (".pkl", ".pickle"):
-        return pd.read_pickle(source)
-    raise NotImplementedError(f"file type of '{source}' is not handled")
-
-
-def _apply_where(df: pd.DataFrame, where_list):
-    """AND of static {"col","comp","val"} dicts (DataLoader._bool_numpy_from_where, dataloader.py:1886-1971)."""
-    if not where_list:
-        return df
-    m = np.ones(len(df), dtype=bool)
-    for w in where_list:
-        col = df[w["col"]].values
-        val = w["val"]
-        if np.issubdtype(col.dtype, np.datetime64) and not isinstance(val, np.datetime64):
-            val = np.datetime64(val)
-        m &= _COMP[w["comp"]](col, val)
-    return df.loc[m]
-
-
-def _where_list(global_select, local_select, ref_row: dict):
-    """DataLoader.get_where_list (dataloader.py:2892-2978)."""
-    out = []
-    for gs in global_select or []:
-        is_static = all(c in gs for c in ("col", "comp", "val"))
-        is_dynamic = all(c in gs for c in ("loc_col", "src_col", "func"))
-        assert is_static or is_dynamic, f"global_select entry not understood: {gs}"
-        if is_static:
-            out.append(dict(gs))
-            continue
-        func = gs["func"]
-        if isinstance(func, str):
-            func = eval(func, {"np": np, "pd": pd})  # noqa: S307  same contract as the reference's config lambdas
-        for ls in local_select:
-            if gs["loc_col"] == ls["col"]:
-                out.append({"col": gs["src_col"], "comp": ls["comp"], "val": func(ref_row[gs["loc_col"]], ls["val"])})
+def json_serializable(d, max_len_df=100):
+    """dict -> dict that json.dumps accepts (GPSat/utils.py:1331-1434): tuple keys and unknown objects become
+    strings, arrays lists, short frames dicts."""
+    assert isinstance(d, dict), f"input is type: {type(d)}, expect dict"
+    out = {}
+    for k, v in d.items():
+        if isinstance(k, tuple):
+            k = str(k)
+        if isinstance(v, dict):
+            out[k] = json_serializable(v, max_len_df)
+        elif isinstance(v, np.ndarray):
+            out[k] = v.tolist()
+        elif isinstance(v, (pd.DataFrame, pd.Series)):
+            out[k] = json_serializable(v.to_dict(), max_len_df) if len(v) <= max_len_df else str(v)
+        else:
+            try:
+                json.dumps({k: v})
+                out[k] = v
+            except (TypeError, OverflowError):
+                out[k] = str(v)
     return out
 
 
-def _json_default(o):
-    if isinstance(o, np.ndarray):
-        return o.tolist()
-    if isinstance(o, (np.integer,)):
-        return int(o)
-    if isinstance(o, (np.floating,)):
-        return float(o)
-    if isinstance(o, pd.DataFrame):
-        return f"<DataFrame shape={o.shape}>"
-    return str(o)
+def nested_dict_literal_eval(d):
+    """inverse of json_serializable's tuple-key stringification (GPSat/utils.py:1276-1328); in place"""
+    for k in list(d.keys()):
+        if isinstance(k, str) and re.search(r"^\(.*\)$", k):
+            try:
+                ke = literal_eval(k)
+                if ke != k:
+                    d[ke] = d.pop(k)
+                    k = ke
+            except ValueError:
+                pass
+        if isinstance(d[k], dict):
+            d[k] = nested_dict_literal_eval(d[k])
+    return d
+
+
+# ---------------------------------------------------------------------------------------------
+# oi_config bookkeeping (GPSat/utils.py:1136-1327)
+# ---------------------------------------------------------------------------------------------
+def get_previous_oi_config(store_path, oi_config, table_name="oi_config", skip_valid_checks_on=None):
+    """Returns (previous config(s), skip_valid_checks_on, config_id) and appends the current config to the
+    ``oi_config`` table when it is new (first run: idx 1; no exact match among the stored ones: max idx + 1)."""
+    skip_valid_checks_on = [] if skip_valid_checks_on is None else skip_valid_checks_on
+    row = pd.DataFrame({"idx": 1, "datetime": datetime.datetime.now().strftime("%Y-%m-%d %H:%M:%S"),
+                        "config": json.dumps(json_serializable(oi_config))}, index=[1])
+    append_kw = dict(index=False, data_columns=["idx", "datetime"], min_itemsize={"config": 50000})
+    exists = False
+    if os.path.exists(store_path):
+        with pd.HDFStore(store_path, mode="r") as store:
+            exists = table_name in store
+    if not exists:
+        with pd.HDFStore(store_path, mode="a") as store:
+            store.append(key=table_name, value=row, **append_kw)
+            try:
+                store.get_storer(table_name).attrs["oi_config"] = oi_config
+            except Exception as e:     # the attribute is a convenience copy; the table row is authoritative
+                print(e)
+        return oi_config, skip_valid_checks_on, 1
+    with pd.HDFStore(store_path, mode="a") as store:
+        prev = {r["idx"]: nested_dict_literal_eval(json.loads(r["config"])) for _, r in store.get(table_name).iterrows()}
+        current = nested_dict_literal_eval(json.loads(row["config"].iloc[0]))
+        same = [k for k, v in prev.items() if v == oi_config or v == current]
+        if same:
+            return prev[max(same)], skip_valid_checks_on, int(max(same))
+        row["idx"] = max(prev) + 1
+        store.append(key=table_name, value=row, **append_kw)
+        return prev, skip_valid_checks_on, int(row["idx"].values[0])
+
+
+def check_prev_oi_config(prev_oi_config, oi_config, skip_valid_checks_on=None):
+    """AssertionError when a key of the current config differs from the previous run's (utils.py:1276-1327 documents
+    this; as written the reference's final assert is inverted and a non-matching config dies on a KeyError instead --
+    the outcome, "a store is not silently continued with another config", is the same)."""
+    skip = [] if skip_valid_checks_on is None else skip_valid_checks_on
+    if prev_oi_config == oi_config:
+        return
+    if prev_oi_config and all(isinstance(k, (int, np.integer)) for k in prev_oi_config):
+        prev_oi_config = prev_oi_config[max(prev_oi_config)]        # {idx: config}: compare with the latest
+    cur = nested_dict_literal_eval(json.loads(json.dumps(json_serializable(oi_config))))
+    bad = [k for k, v in cur.items() if k not in skip and v != prev_oi_config.get(k)]
+    assert len(bad) == 0, f"the following keys did not have values that matched exactly: {bad}"
+
+
+def remove_previously_run_locations(store_path, xprt_locs, table="run_details"):
+    """Anti-join of the expert locations with the index of ``table`` in the store (local_experts.py:474-497)."""
+    try:
+        with pd.HDFStore(store_path, mode="r") as store:
+            prev = store.select(table)
+        names = list(prev.index.names)
+        prev = prev.reset_index()[names].drop_duplicates()
+        tmp = xprt_locs.merge(prev, how="left", on=names, indicator="found_already")
+        keep = (tmp["found_already"] == "left_only").values
+        print(f"for table: {table} returning {keep.sum()} / {len(keep)} entries")
+        return xprt_locs.loc[keep].copy(True)
+    except (OSError, KeyError) as e:
+        print(e)
+        return xprt_locs
 
 
 class LocalExpertOI:
@@ -109,6 +158,9 @@ class LocalExpertOI:
             expert_loc_config = local_expert_config
         self.config = {}
         self.device = device
+        self.expert_locs = None
+        self.model = None
+        self.data_source = None
         self.set_expert_locations(**(expert_loc_config or {}))
         self.set_data(**(data_config or {}))
         self.set_model(**(model_config or {}))
@@ -118,58 +170,65 @@ class LocalExpertOI:
     def set_expert_locations(self, df=None, file=None, source=None, where=None, add_data_to_col=None,
                              col_funcs=None, keep_cols=None, col_select=None, row_select=None, sort_by=None,
                              reset_index=False, source_kwargs=None, verbose=False, **kwargs):
-        self.config["locations"] = {k: v for k, v in dict(file=file, source=source, where=where,
-                                                          row_select=row_select, sort_by=sort_by).items()
-                                    if v is not None and not isinstance(v, pd.DataFrame)}
-        src = df if df is not None else (source if source is not None else file)
-        if src is None:
-            self.expert_locs = None
+        if col_select is None and keep_cols is not None:
+            warnings.warn("\n'keep_cols' provided to set_expert_locations, use 'col_select' instead")
+            col_select = keep_cols
+        if source is None and df is not None:
+            warnings.warn("\n'df' was provided to set_expert_locations, use 'source' instead")
+            source = df
+        if source is None and file is not None:
+            warnings.warn("\n'file' was provided to set_expert_locations, use 'source' instead")
+            source = file
+        if source is None:
             return
-        locs = _load_frame(src).copy()
-        for k, v in (add_data_to_col or {}).items():
-            locs[k] = v
-        rs = row_select if row_select is not None else where
-        if rs:
-            locs = _apply_where(locs, rs if isinstance(rs, list) else [rs])
-        cs = col_select if col_select is not None else keep_cols
-        if cs:
-            locs = locs[cs]
+        self.config["locations"] = json_serializable(dict(
+            df=df, file=file, source=source, where=where, add_data_to_col=add_data_to_col, col_funcs=col_funcs,
+            keep_cols=keep_cols, col_select=col_select, row_select=row_select, sort_by=sort_by,
+            reset_index=reset_index, source_kwargs=source_kwargs, verbose=verbose, **kwargs))
+        locs = dl.load(source=source, where=where, source_kwargs=source_kwargs, col_funcs=col_funcs,
+                       row_select=row_select, col_select=col_select, reset_index=reset_index,
+                       add_data_to_col=add_data_to_col, **kwargs)
         if sort_by:
             locs = locs.sort_values(sort_by)
-        if reset_index:
-            locs = locs.reset_index(drop=True)
         self.expert_locs = locs
 
     def set_data(self, data_source=None, table=None, obs_col=None, coords_col=None, local_select=None,
-                 global_select=None, row_select=None, col_select=None, col_funcs=None, engine=None,
+                 global_select=None, where=None, row_select=None, col_select=None, col_funcs=None, engine=None,
                  read_kwargs=None, **kwargs):
-        assert col_funcs is None, "col_funcs are not applied by the batched driver: pre-compute the columns"
-        self.data_source, self.data_table = data_source, table
+        self.config["data"] = json_serializable({k: v for k, v in dict(
+            data_source=data_source, table=table, obs_col=obs_col, coords_col=coords_col, local_select=local_select,
+            global_select=global_select, where=where, row_select=row_select, col_select=col_select,
+            col_funcs=col_funcs, engine=engine, read_kwargs=read_kwargs, **kwargs).items()
+            if not (v is None and k in ("where", "engine", "read_kwargs"))})
+        self.data_table = table
         self.obs_col = obs_col[0] if isinstance(obs_col, (list, tuple)) and len(obs_col) == 1 else obs_col
         self.coords_col = [coords_col] if isinstance(coords_col, str) else coords_col
         self.local_select, self.global_select = local_select, global_select or []
-        self.row_select, self.col_select = row_select, col_select
-        self.config["data"] = {k: v for k, v in dict(data_source=data_source, table=table, obs_col=obs_col,
-                                                     coords_col=coords_col, local_select=local_select,
-                                                     global_select=global_select, row_select=row_select,
-                                                     col_select=col_select).items()
-                               if not isinstance(v, pd.DataFrame)}
+        self.data_where = where
+        self.row_select, self.col_select, self.col_funcs = row_select, col_select, col_funcs
+        # a path is opened once (HDFStore stays open read-only for the run, like LocalExpertData.set_data_source)
+        self.data_source = dl.open_source(data_source, engine, **(read_kwargs or {})) \
+            if isinstance(data_source, str) else data_source
 
     def set_model(self, oi_model=None, init_params=None, constraints=None, load_params=None, optim_kwargs=None,
                   pred_kwargs=None, params_to_store=None, replacement_threshold=None, replacement_model=None,
                   replacement_init_params=None, replacement_constraints=None, replacement_optim_kwargs=None,
                   replacement_pred_kwargs=None):
-        self.config["model"] = dict(oi_model=oi_model, init_params=init_params, constraints=constraints,
-                                    load_params=load_params, optim_kwargs=optim_kwargs, pred_kwargs=pred_kwargs,
-                                    params_to_store=params_to_store)
+        self.config["model"] = json_serializable(dict(
+            oi_model=oi_model, init_params=init_params, constraints=constraints, load_params=load_params,
+            optim_kwargs=optim_kwargs, pred_kwargs=pred_kwargs, params_to_store=params_to_store,
+            replacement_threshold=replacement_threshold, replacement_model=replacement_model,
+            replacement_init_params=replacement_init_params, replacement_constraints=replacement_constraints,
+            replacement_optim_kwargs=replacement_optim_kwargs, replacement_pred_kwargs=replacement_pred_kwargs))
         if oi_model is None:
             self.model = None
             return
         if isinstance(oi_model, str):
             self.model = _get_model(oi_model)
-        elif isinstance(oi_model, dict):
-            import importlib
-            self.model = getattr(importlib.import_module(oi_model["path_to_model"]), oi_model["model_name"])
+        elif isinstance(oi_model, dict):         # the reference's custom-model hook (local_experts.py:319-325)
+            path = oi_model["path_to_model"]
+            sys.path.append(path)
+            self.model = getattr(importlib.import_module(path), oi_model["model_name"])
         else:
             self.model = oi_model
         assert self.model in (B200GPRModel, B200SGPRModel), "the batched driver dispatches B200GPRModel / B200SGPRModel"
@@ -183,194 +242,291 @@ class LocalExpertOI:
         if load_params is not None:
             assert not load_params.get("previous", False), \
                 "load_params={'previous': True} makes experts order-dependent and cannot be batched"
-        self.params_to_store = params_to_store
+        self.params_to_store = None if params_to_store == "all" else params_to_store
 
     def set_pred_loc(self, method="expert_loc", coords_col=None, df=None, df_file=None, max_dist=None,
                      copy_df=False, **kwargs):
-        self.config["pred_loc"] = {k: v for k, v in dict(method=method, df_file=df_file, max_dist=max_dist).items()
-                                   if v is not None}
+        self.config["pred_loc"] = json_serializable(dict(method=method, coords_col=coords_col, df=df, df_file=df_file,
+                                                         max_dist=max_dist, copy_df=copy_df, **kwargs))
         assert method in ("expert_loc", "from_dataframe"), f"pred_loc method '{method}' is not handled"
         self.pred_method, self.pred_max_dist = method, max_dist
         self.pred_df = None
         if method == "from_dataframe":
-            self.pred_df = df if df is not None else _load_frame(df_file)
+            if df is None:       # prediction_locations.py:213-218
+                assert isinstance(df_file, str), f"df is None, df_file expected to be str, got: {type(df_file)}"
+                df = pd.read_csv(df_file)
+            self.pred_df = df
 
     # ---- parameter loading (local_experts.py:553-689), vectorised over experts ----
-    def _load_theta(self, locs: pd.DataFrame, store_tables=None):
+    def _same_param_table(self, store_path, table_suffix):
+        """local_experts.py:749-759: loading from and (not optimising) writing to the same table"""
         lp = self.load_params_config
+        extra = [k for k in lp if k not in ("file", "table_suffix")]
+        return (store_path == lp.get("file", None)) and (table_suffix == lp.get("table_suffix", None)) \
+            and len(extra) == 0
+
+    def _load_theta(self, locs: pd.DataFrame):
+        """Per-expert start values [E, D+2] and a mask of experts that can run.
+
+        ``load_params`` forms (local_experts.py:553-606): ``file`` (+ ``table_suffix``, ``param_names``,
+        ``index_adjust``) -> one lookup per parameter table keyed on the expert's coords_col values; otherwise the
+        remaining keys are fixed values applied to every expert (``set_parameters(**param_dict)``).  A parameter that
+        is missing or NaN for an expert keeps the model default; an expert for which the file yields nothing at all
+        is skipped (status 1, local_experts.py:595-596,1099-1101)."""
+        lp = self.load_params_config
+        E, D = len(locs), len(self.coords_col)
         if lp is None:
-            return None, np.ones(len(locs), dtype=bool)
-        D = len(self.coords_col)
-        theta = np.full((len(locs), D + 2), np.nan)
-        suffix = lp.get("table_suffix", "")
-        src = lp.get("file", None)
-        tables = store_tables if (src is None and store_tables is not None) else None
+            return None, np.ones(E, dtype=bool)
+        spec = ModelSpec.from_model_config(self.model_config)
+        default = HyperParams(D, spec.lengthscales, spec.kernel_variance, spec.likelihood_variance).theta()
+        theta = np.tile(default, (E, 1))
         sl = {"lengthscales": slice(0, D), "kernel_variance": slice(D, D + 1),
               "likelihood_variance": slice(D + 1, D + 2)}
-        names = lp.get("param_names") or PARAM_NAMES
-        key = locs[self.coords_col].reset_index(drop=True)
-        key["_row_"] = np.arange(len(key))
+        src = lp.get("file", None)
+        if src is None:
+            fixed = {k: v for k, v in lp.items() if k not in ("previous", "previous_params", "file", "param_names",
+                                                              "ref_loc", "index_adjust", "table_suffix")}
+            for nm, v in fixed.items():
+                assert nm in sl, f"cannot set parameter '{nm}': not one of {list(sl)}"
+                theta[:, sl[nm]] = np.broadcast_to(np.asarray(v, dtype=np.float64).ravel(), (sl[nm].stop - sl[nm].start,))
+            return theta, np.ones(E, dtype=bool)
+        suffix = lp.get("table_suffix", "")
+        names = lp.get("param_names") or list(PARAM_NAMES)
         for nm in names:
-            if isinstance(src, dict):
-                df = src[f"{nm}{suffix}"]
-            elif tables is not None:
-                df = tables[f"{nm}{suffix}"]
-            else:
-                df = pd.read_hdf(src, key=f"{nm}{suffix}")
-            df = df.reset_index()
-            m = key.merge(df, how="left", on=self.coords_col)
-            if "_dim_0" in m.columns:
-                m = m.sort_values(["_row_", "_dim_0"])
-            vals = m[nm].values.reshape(len(key), -1)
-            theta[:, sl[nm]] = vals
-        ok = ~np.isnan(theta[:, [sl[n].start for n in names]]).any(axis=1)
-        # parameters not loaded keep the model defaults
-        spec = ModelSpec.from_model_config(self.model_config)
-        from .params import HyperParams
-        d = HyperParams(D, spec.lengthscales, spec.kernel_variance, spec.likelihood_variance).theta()
-        for j in range(D + 2):
-            col = theta[:, j]
-            col[np.isnan(col) & ok] = d[j]
-        return theta, ok
+            assert nm in sl, f"provide param name:{nm}\nis not in param_names:{list(sl)} handled by the batched loader"
+        key = locs[self.coords_col].reset_index(drop=True).copy()
+        for c, spec_c in (lp.get("index_adjust") or {}).items():        # e.g. parameters of the previous day
+            key[c] = [dl.config_func(**spec_c, args=v) for v in key[c].values]
+        key["_row_"] = np.arange(E)
+        found_any = np.zeros(E, dtype=bool)
+        if isinstance(src, str):
+            assert os.path.exists(src), f"in load_params file provided:\n{src}\nbut path does not exist"
+        for nm in names:
+            try:
+                if isinstance(src, dict):           # in-memory tables (tests, chained runs)
+                    tab = src[f"{nm}{suffix}"]
+                else:
+                    with pd.HDFStore(src, mode="r") as store:
+                        tab = store.select(f"{nm}{suffix}")
+            except KeyError as e:
+                print("KeyError\n", e, f"\nskipping param_name: {nm}")
+                continue
+            tab = tab.reset_index()
+            if "_dim_0" not in tab.columns:
+                tab["_dim_0"] = 0
+            width = sl[nm].stop - sl[nm].start
+            m = key.merge(tab[self.coords_col + ["_dim_0", nm]], how="inner", on=self.coords_col)
+            m = m[(m["_dim_0"] >= 0) & (m["_dim_0"] < width)]
+            vals = np.full((E, width), np.nan)
+            vals[m["_row_"].values, m["_dim_0"].values.astype(int)] = m[nm].values
+            got = ~np.isnan(vals).any(axis=1)         # a NaN anywhere drops the parameter for that expert
+            theta[got, sl[nm]] = vals[got]
+            found_any |= got
+        return theta, found_any
 
     # ---- the run ----
     def run(self, store_path=None, store_every=10, check_config_compatible=True, skip_valid_checks_on=None,
-            optimise=True, predict=True, min_obs=3, table_suffix="", return_tables=None):
-        """Same arguments as the reference's ``run`` (local_experts.py:761-769).  Tables are appended to the
-        HDF5 file at ``store_path`` (pandas.HDFStore, needs PyTables like the reference); with
-        ``store_path=None`` or ``return_tables=True`` they are returned as a dict of DataFrames."""
+            optimise=True, predict=True, min_obs=3, table_suffix="", return_tables=None, max_batch=4096):
+        """Same arguments as the reference's ``run`` (local_experts.py:761-769) plus ``max_batch`` (experts per
+        engine chunk = flush unit) and ``return_tables``.  Tables are appended to the HDF5 file at ``store_path``
+        (pandas.HDFStore, needs PyTables like the reference); with ``store_path=None`` or ``return_tables=True``
+        they are returned as a dict of DataFrames."""
         from . import get_engine
+        import torch.distributed as dist
         t_run = time.perf_counter()
+        assert isinstance(self.expert_locs, pd.DataFrame), \
+            f"attr expert_locs is {type(self.expert_locs)}, expected to be DataFrame"
+        assert self.data_source is not None, "'data_source' is None"
         assert self.model is not None, "'model' is None"
-        assert self.expert_locs is not None, "expert locations were not provided"
-        min_obs, store_every = int(min_obs), int(store_every)
+        min_obs, store_every, max_batch = int(min_obs), int(store_every), int(max_batch)
+        assert store_every >= 1, f"store_every must be >= 1, got: {store_every}"
         assert min_obs >= 1, f"min_obs must be >= 1, got: {min_obs}"
+        assert max_batch >= 1
         if return_tables is None:
             return_tables = store_path is None
+        self.config["run_kwargs"] = json_serializable(dict(
+            store_path=store_path, store_every=store_every, check_config_compatible=check_config_compatible,
+            skip_valid_checks_on=skip_valid_checks_on, optimise=optimise, predict=predict, min_obs=min_obs,
+            table_suffix=table_suffix))
+        multi = dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
+        is_writer = (not multi) or dist.get_rank() == 0
+        coords_col = self.coords_col
+        out_tables = {}
+
+        # ---- store bookkeeping: config id, expert_locs table, resume (local_experts.py:862-912) ----
+        config_id, keep_pos = 1, None
+        if store_path is not None and is_writer:
+            os.makedirs(os.path.dirname(os.path.abspath(store_path)), exist_ok=True)
+            prev_cfg, skip_valid_checks_on, config_id = get_previous_oi_config(
+                store_path, self.config, skip_valid_checks_on=skip_valid_checks_on,
+                table_name=f"oi_config{table_suffix}")
+            if check_config_compatible:
+                check_prev_oi_config(prev_cfg, self.config, skip_valid_checks_on)
+            store_locs = remove_previously_run_locations(store_path, self.expert_locs.copy(True),
+                                                         table=f"expert_locs{table_suffix}")
+            store_locs = store_locs.set_index(coords_col)
+            with pd.HDFStore(store_path, mode="a") as store:
+                store.append(f"expert_locs{table_suffix}", store_locs, data_columns=True)
+            left = remove_previously_run_locations(store_path, self.expert_locs.copy(True).assign(
+                _pos_=np.arange(len(self.expert_locs))), table=f"run_details{table_suffix}")
+            keep_pos = left["_pos_"].values
+        if multi:      # one reader / writer of the store: rank 0 decides, everybody follows
+            box = [config_id, keep_pos]
+            dist.broadcast_object_list(box, src=0)
+            config_id, keep_pos = box
+        xprt = self.expert_locs.copy(True)
+        if keep_pos is not None:
+            xprt = xprt.iloc[keep_pos]
+        if store_path is None:
+            out_tables[f"expert_locs{table_suffix}"] = self.expert_locs.set_index(coords_col)
+            out_tables[f"oi_config{table_suffix}"] = pd.DataFrame(
+                {"idx": config_id, "datetime": datetime.datetime.now().strftime("%Y-%m-%d %H:%M:%S"),
+                 "config": json.dumps(json_serializable(self.config))}, index=[config_id])
+
         eng = get_engine(self.device)
         spec = ModelSpec.from_model_config(self.model_config)
-        coords_col, obs_col = self.coords_col, self.obs_col
         D = len(coords_col)
-        self.config["run_kwargs"] = dict(optimise=optimise, predict=predict, min_obs=min_obs,
-                                         table_suffix=table_suffix)
-        config_id = 1
-        src = _load_frame(self.data_source, self.data_table)
-        if self.row_select:
-            src = _apply_where(src, self.row_select)
-        xprt = self.expert_locs.copy(True)
-        # resume: drop experts already present in run_details (local_experts.py:474-497, 905-912)
-        prev_tables = None
-        if store_path is not None and os.path.exists(store_path):
-            try:
-                with pd.HDFStore(store_path, mode="r") as st:
-                    if f"/run_details{table_suffix}" in st.keys():
-                        prev = st.get(f"run_details{table_suffix}").reset_index()[coords_col]
-                        tmp = xprt.merge(prev.drop_duplicates(), how="left", on=coords_col, indicator="found_already")
-                        xprt = xprt.loc[(tmp["found_already"] == "left_only").values].copy(True)
-                    if f"/oi_config{table_suffix}" in st.keys():
-                        config_id = int(st.get(f"oi_config{table_suffix}")["idx"].max()) + 1
-            except Exception as e:      # same spirit as the reference's try/except-and-print
-                print(e)
-        # group experts by their global where list (local_experts.py:426-472)
-        rows = xprt.to_dict("records")
-        groups, order = {}, []
-        for i, r in enumerate(rows):
-            w = _where_list(self.global_select, self.local_select, r)
-            k = json.dumps(w, default=_json_default, sort_keys=True)
-            if k not in groups:
-                groups[k] = (w, [])
-                order.append(k)
-            groups[k][1].append(i)
         model_name = pretty_print_class(self.model)[:64]
         dev_name = self._device_name()[:64]
-        table_cols = list(dict.fromkeys(list(coords_col) + [obs_col] + [c for ls in self.local_select
-                                                                         for c in ([ls["col"]] if isinstance(ls["col"], str) else ls["col"])]))
-        ref_cols = [c for c in xprt.columns if np.issubdtype(xprt[c].dtype, np.number)]
+        sel_cols = [c for ls in self.local_select for c in ([ls["col"]] if isinstance(ls["col"], str) else ls["col"])]
+        table_cols = list(dict.fromkeys(list(coords_col) + [self.obs_col] + sel_cols))
         pred_cols, pred_tab = None, None
         if self.pred_method == "from_dataframe":
             pred_cols = [c for c in coords_col if c in self.pred_df.columns]
             pred_tab = np.ascontiguousarray(self.pred_df[pred_cols].values.T, dtype=np.float64)
-        pieces = {}          # table name -> list of (first expert position, DataFrame)
-        for k in order:
-            where, members = groups[k]
-            gdf = _apply_where(src, where).reset_index(drop=True)
-            if self.col_select:
-                gdf = gdf[self.col_select]
-            t0 = time.perf_counter()
-            table = np.ascontiguousarray(gdf[table_cols].values.T, dtype=np.float64)
-            sub = xprt.iloc[members]
-            refs = np.ascontiguousarray(sub[ref_cols].values, dtype=np.float64)
-            theta_init, ok_load = self._load_theta(sub)
-            if len(gdf) == 0:
-                table = np.zeros((len(table_cols), 1)) + np.inf     # nothing can be selected
-            # one process per GPU: the expert list is sharded by N^3 cost and gathered once (distributed.py)
-            res = run_experts_sharded(eng, spec, table, table_cols, obs_col, coords_col, refs, ref_cols,
-                                      self.local_select, pred_table=pred_tab, pred_cols=pred_cols,
-                                      max_dist=self.pred_max_dist, optimise=optimise, predict=predict,
-                                      min_obs=min_obs, theta_init=theta_init)
-            dt = time.perf_counter() - t0
-            self._shape_tables(pieces, res, sub, members, ok_load, dt, optimise, predict, model_name, dev_name,
-                               config_id, D)
-        tables = {}
-        for name, lst in pieces.items():
-            # rows back in the order the sequential loop would have appended them
-            df = pd.concat([t[1] for t in lst], axis=0)
-            if len(lst) > 1:
-                df = df.iloc[np.argsort(df["_pos_"].values, kind="stable")]
-            tables[f"{name}{table_suffix}"] = df.drop(columns="_pos_")
-        # expert_locs + oi_config bookkeeping (local_experts.py:873-903; utils.py:1136-1273)
-        tables[f"expert_locs{table_suffix}"] = self.expert_locs.set_index(coords_col)
-        tables[f"oi_config{table_suffix}"] = pd.DataFrame(
-            {"idx": [config_id], "datetime": [datetime.datetime.now().strftime("%Y-%m-%d %H:%M:%S")],
-             "config": [json.dumps(self.config, default=_json_default)]}).set_index("idx", drop=False)
-        import torch.distributed as dist
-        is_writer = not (dist.is_available() and dist.is_initialized()) or dist.get_rank() == 0
-        if store_path is not None and is_writer:
-            self._write(store_path, tables)
+        # only the columns the kernels read travel to the device (the C ABI takes at most 16 reference columns)
+        ref_cols = [c for c in dict.fromkeys(list(coords_col) + sel_cols)
+                    if c in xprt.columns and np.issubdtype(xprt[c].dtype, np.number)]
+        assert all(c in ref_cols for c in coords_col), "expert locations must hold every (numeric) coords_col"
+        save_params = not (self.load_params_config is not None and (not optimise)
+                           and self._same_param_table(store_path, table_suffix))
+        rows = xprt.to_dict("records")
+        cache_key, cache_df = None, None
+        for c0 in range(0, len(xprt), max_batch):
+            members_all = np.arange(c0, min(c0 + max_batch, len(xprt)))
+            # group the chunk's experts by their global where list (local_experts.py:426-472)
+            groups, order = {}, []
+            for i in members_all:
+                w = dl.get_where_list(self.global_select, self.local_select, rows[i])
+                k = json.dumps(w, default=str, sort_keys=True)
+                if k not in groups:
+                    groups[k] = (w, [])
+                    order.append(k)
+                groups[k][1].append(i)
+            pieces = {}
+            for k in order:
+                where, members = groups[k]
+                if k != cache_key:
+                    base = ([self.data_where] if isinstance(self.data_where, dict) else list(self.data_where or []))
+                    cache_df = dl.load(source=self.data_source, table=self.data_table, where=base + where,
+                                       col_funcs=self.col_funcs, row_select=self.row_select,
+                                       col_select=self.col_select, reset_index=True)
+                    cache_key = k
+                gdf = cache_df
+                t0 = time.perf_counter()
+                if len(gdf):
+                    table = np.ascontiguousarray(gdf[table_cols].values.T, dtype=np.float64)
+                else:
+                    table = np.zeros((len(table_cols), 1)) + np.inf     # nothing can be selected
+                sub = xprt.iloc[members]
+                theta_init, ok_load = self._load_theta(sub)
+                kw = dict(pred_table=pred_tab, pred_cols=pred_cols, max_dist=self.pred_max_dist, min_obs=min_obs)
+                res, res_bad = None, None
+                if ok_load.any():
+                    refs = np.ascontiguousarray(sub[ref_cols].values[ok_load], dtype=np.float64)
+                    # one process per GPU: the expert list is sharded by N^3 cost and gathered once (distributed.py)
+                    res = run_experts_sharded(eng, spec, table, table_cols, self.obs_col, coords_col, refs, ref_cols,
+                                              self.local_select, optimise=optimise, predict=predict,
+                                              theta_init=None if theta_init is None else theta_init[ok_load], **kw)
+                if not ok_load.all():
+                    # experts whose parameters could not be loaded are not run (local_experts.py:1099-1101), but the
+                    # ones with too few observations are still recorded (the min_obs test comes first, :988-1012)
+                    refs = np.ascontiguousarray(sub[ref_cols].values[~ok_load], dtype=np.float64)
+                    res_bad = run_experts_sharded(eng, spec, table, table_cols, self.obs_col, coords_col, refs,
+                                                  ref_cols, self.local_select, count_only=True, **kw)
+                dt = time.perf_counter() - t0
+                self._shape_tables(pieces, res, res_bad, sub, np.asarray(members), ok_load, dt, optimise, predict,
+                                   model_name, dev_name, config_id, D, save_params)
+            chunk = {}
+            # tables in the order the reference's save_dict holds them (run_details, preds, parameters)
+            for name, lst in sorted(pieces.items(), key=lambda kv: {"run_details": 0, "preds": 1}.get(kv[0], 2)):
+                df = pd.concat(lst, axis=0)
+                # rows back in the order the sequential loop would have appended them
+                df = df.iloc[np.argsort(df["_pos_"].values, kind="stable")].drop(columns="_pos_")
+                chunk[f"{name}{table_suffix}"] = df
+            if store_path is not None and is_writer:
+                self._flush(store_path, chunk)
+            if return_tables:
+                for name, df in chunk.items():
+                    out_tables.setdefault(name, []).append(df)
         print(f"'run': {time.perf_counter() - t_run:.3f} seconds")
-        return tables if return_tables else None
+        if not return_tables:
+            return None
+        return {k: (pd.concat(v, axis=0) if isinstance(v, list) else v) for k, v in out_tables.items()}
 
     @classmethod
     def run_from(cls, ref_oi, **run_kwargs):
         """Batched run of an already configured reference ``GPSat.local_experts.LocalExpertOI`` instance
         (the hook shown in INTEGRATION.md): its captured config dicts rebuild the driver."""
         cfg = ref_oi.config
-        oi = cls(expert_loc_config=cfg.get("locations") or cfg.get("local_expert_locations"),
-                 data_config=cfg.get("data"), model_config=cfg.get("model"), pred_loc_config=cfg.get("pred_loc"))
+        model_cfg = dict(cfg.get("model") or {})
+        oi = cls(expert_loc_config=None, data_config=cfg.get("data"), model_config=model_cfg,
+                 pred_loc_config=cfg.get("pred_loc"))
+        locs_cfg = cfg.get("locations") or cfg.get("local_expert_locations")
         if getattr(ref_oi, "expert_locs", None) is not None:
             oi.expert_locs = ref_oi.expert_locs
+            oi.config["locations"] = locs_cfg
+        elif locs_cfg:
+            oi.set_expert_locations(**locs_cfg)
+        data = getattr(ref_oi, "data", None)
+        if data is not None and isinstance(getattr(data, "data_source", None), pd.DataFrame):
+            oi.data_source = data.data_source         # in-memory sources are not part of the JSON-able config
+        pl = getattr(ref_oi, "pred_loc", None)
+        if pl is not None and isinstance(getattr(pl, "kwargs", {}).get("df", None), pd.DataFrame):
+            oi.pred_df = pl.kwargs["df"]
         return oi.run(**run_kwargs)
 
     def _device_name(self):
         import torch
         return torch.cuda.get_device_name(self.device)
 
-    def _shape_tables(self, pieces, res, sub, members, ok_load, dt, optimise, predict, model_name, dev_name,
-                      config_id, D):
+    def _shape_tables(self, pieces, res, res_bad, sub, pos, ok_load, dt, optimise, predict, model_name, dev_name,
+                      config_id, D, save_params):
         """Vectorised dict_of_array_to_table (local_experts.py:691-747) for a whole batch."""
         coords_col = self.coords_col
-        E = len(sub)
-        ref = sub[coords_col].values
-        num_obs = res["num_obs"]
-        too_few = res["too_few"]
-        valid_idx = res.get("valid_idx", np.zeros(0, dtype=np.int64))
-        keep = np.zeros(E, dtype=bool)
-        keep[valid_idx] = True
-        # experts whose parameters could not be loaded are skipped (local_experts.py:1099-1101)
-        keep &= ok_load
-        recorded = keep | too_few
-        pos = np.asarray(members)
-        Ev = len(valid_idx)
-        vpos = np.full(E, -1)
-        vpos[valid_idx] = np.arange(Ev)
+        ref_all = sub[coords_col].values
 
         def midx(rows_ref):
             if len(coords_col) == 1:
                 return pd.Index(rows_ref[:, 0], name=coords_col[0])
             return pd.MultiIndex.from_arrays([rows_ref[:, j] for j in range(len(coords_col))], names=coords_col)
 
-        # run_details
-        r = np.flatnonzero(recorded)
+        def details(r, num_obs, rt, fobj, succ, ran, ref, pp):
+            return pd.DataFrame({"_dim_0": 0, "num_obs": num_obs[r], "run_time": rt[r],
+                                 "objective_value": fobj[r], "parameters_optimised": optimise,
+                                 "optimise_success": succ[r], "model": model_name,
+                                 "device": np.where(ran[r], dev_name, ""), "config_id": config_id,
+                                 "_pos_": pp[r]}, index=midx(ref[r]))
+
+        if res_bad is not None:         # parameters missing: only the "too few observations" rows are recorded
+            b = np.flatnonzero(~ok_load)
+            r = np.flatnonzero(res_bad["too_few"])
+            if len(r):
+                nanv, f = np.full(len(b), np.nan), np.zeros(len(b), dtype=bool)
+                pieces.setdefault("run_details", []).append(
+                    details(r, res_bad["num_obs"], nanv, nanv, f, f, ref_all[b], pos[b]))
+        if res is None:
+            return
+        g = np.flatnonzero(ok_load)
+        ref, pp = ref_all[g], pos[g]
+        E = len(g)
+        num_obs, too_few = res["num_obs"], res["too_few"]
+        valid_idx = res.get("valid_idx", np.zeros(0, dtype=np.int64))
+        Ev = len(valid_idx)
+        keep = np.zeros(E, dtype=bool)
+        keep[valid_idx] = True
+        vpos = np.full(E, -1)
+        vpos[valid_idx] = np.arange(Ev)
         fobj = np.full(E, np.nan)
         succ = np.zeros(E, dtype=bool)
         if Ev:
@@ -378,80 +534,108 @@ class LocalExpertOI:
             if optimise:
                 succ[valid_idx] = np.isin(res["status"], (1, 2))
         rt = np.where(keep, dt / max(int(keep.sum()), 1), np.nan)
-        rd = pd.DataFrame({"_dim_0": 0, "num_obs": num_obs[r], "run_time": rt[r],
-                           "objective_value": np.where(keep[r], fobj[r], np.nan),
-                           "parameters_optimised": optimise, "optimise_success": succ[r] & keep[r],
-                           "model": model_name, "device": np.where(keep[r], dev_name, ""),
-                           "config_id": config_id, "_pos_": pos[r]}, index=midx(ref[r]))
+        r = np.flatnonzero(keep | too_few)
         if len(r):
-            pieces.setdefault("run_details", []).append((pos[r[0]], rd))
+            pieces.setdefault("run_details", []).append(details(r, num_obs, rt, fobj, succ, keep, ref, pp))
         k = np.flatnonzero(keep)
         if len(k) == 0:
             return
-        first = pos[k[0]]
-        same_table = False
-        lp = self.load_params_config
-        if lp is not None and not optimise:
-            same_table = lp.get("file") is None
         # hyper-parameter tables (skipped when loading from and writing to the same table without optimising)
-        if not same_table:
+        if save_params:
             th = res["theta"][vpos[k]]
-            names = self.params_to_store or PARAM_NAMES
+            names = self.params_to_store or (list(PARAM_NAMES) + ["inducing_points"])
             if "lengthscales" in names:
-                pieces.setdefault("lengthscales", []).append((first, pd.DataFrame(
+                pieces.setdefault("lengthscales", []).append(pd.DataFrame(
                     {"_dim_0": np.tile(np.arange(D), len(k)), "lengthscales": th[:, :D].ravel(),
-                     "_pos_": np.repeat(pos[k], D)},
-                    index=midx(np.repeat(ref[k], D, axis=0)))))
+                     "_pos_": np.repeat(pp[k], D)}, index=midx(np.repeat(ref[k], D, axis=0))))
             if "kernel_variance" in names:
-                pieces.setdefault("kernel_variance", []).append((first, pd.DataFrame(
-                    {"_dim_0": 0, "kernel_variance": th[:, D], "_pos_": pos[k]}, index=midx(ref[k]))))
+                pieces.setdefault("kernel_variance", []).append(pd.DataFrame(
+                    {"_dim_0": 0, "kernel_variance": th[:, D], "_pos_": pp[k]}, index=midx(ref[k])))
             if "likelihood_variance" in names:
-                pieces.setdefault("likelihood_variance", []).append((first, pd.DataFrame(
-                    {"_dim_0": 0, "likelihood_variance": th[:, D + 1], "_pos_": pos[k]}, index=midx(ref[k]))))
-            if "inducing_points" in res and (self.params_to_store is None or "inducing_points" in names):
-                zo = res["z_offsets"]
-                zc = res["inducing_points"]
+                pieces.setdefault("likelihood_variance", []).append(pd.DataFrame(
+                    {"_dim_0": 0, "likelihood_variance": th[:, D + 1], "_pos_": pp[k]}, index=midx(ref[k])))
+            if "inducing_points" in res and "inducing_points" in names:
+                zo, zc = res["z_offsets"], res["inducing_points"]
                 mk = np.diff(zo)[vpos[k]]
                 rows = np.concatenate([np.arange(zo[v], zo[v + 1]) for v in vpos[k]])
                 d0 = np.concatenate([np.repeat(np.arange(m), D) for m in mk])
-                pieces.setdefault("inducing_points", []).append((first, pd.DataFrame(
+                pieces.setdefault("inducing_points", []).append(pd.DataFrame(
                     {"_dim_0": d0, "_dim_1": np.tile(np.arange(D), len(rows)), "inducing_points": zc[rows].ravel(),
-                     "_pos_": np.repeat(pos[k], mk * D)}, index=midx(np.repeat(ref[k], mk * D, axis=0)))))
-        # preds
+                     "_pos_": np.repeat(pp[k], mk * D)}, index=midx(np.repeat(ref[k], mk * D, axis=0))))
         if predict:
             poff = res["pred_offsets"]
-            cnt = np.diff(poff)
-            sel = np.concatenate([np.arange(poff[v], poff[v + 1]) for v in vpos[k]]) if len(k) else np.zeros(0, int)
-            cntk = cnt[vpos[k]]
-            dim0 = np.concatenate([np.arange(c) for c in cntk]) if len(k) else np.zeros(0, int)
-            om = res["obs_mean"][vpos[k]]
+            cntk = np.diff(poff)[vpos[k]]
+            sel = np.concatenate([np.arange(poff[v], poff[v + 1]) for v in vpos[k]])
+            dim0 = np.concatenate([np.arange(c) for c in cntk])
             pr = {"_dim_0": dim0, "f*": res["fmean"][sel], "f*_var": res["fvar"][sel], "y_var": res["yvar"][sel],
-                  "f_bar": np.repeat(om, cntk)}
+                  "f_bar": np.repeat(res["obs_mean"][vpos[k]], cntk)}
             for ci, c in enumerate(coords_col):
                 pr[f"pred_loc_{c}"] = res["pred_coords"][sel, ci]
-            pr["_pos_"] = np.repeat(pos[k], cntk)
-            pieces.setdefault("preds", []).append((first, pd.DataFrame(pr, index=midx(np.repeat(ref[k], cntk, axis=0)))))
+            pr["_pos_"] = np.repeat(pp[k], cntk)
+            pieces.setdefault("preds", []).append(pd.DataFrame(pr, index=midx(np.repeat(ref[k], cntk, axis=0))))
 
     @staticmethod
-    def _write(store_path, tables):
-        os.makedirs(os.path.dirname(os.path.abspath(store_path)), exist_ok=True)
-        with pd.HDFStore(store_path, mode="a") as store:     # raises ImportError without PyTables
-            for k, v in tables.items():
-                if k.startswith("expert_locs") and f"/{k}" in store.keys():
-                    continue
-                min_itemsize = {c: 64 for c in v.columns if c in ["model", "device"]}
+    def _flush(store_path, tables):
+        """One HDFStore.append per table with the reference's keyword arguments (local_experts.py:535-543)."""
+        for k, v in tables.items():
+            min_itemsize = {c: 64 for c in v.columns if c in ["model", "device"]}
+            try:
+                with pd.HDFStore(store_path, mode="a") as store:     # raises ImportError without PyTables
+                    store.append(key=k, value=v, min_itemsize=min_itemsize)
+            except ValueError as e:
+                print(e)
+
+
+def get_results_from_h5file(results_file, global_col_funcs=None, merge_on_expert_locations=True,
+                            select_tables=None, table_suffix="", add_suffix_to_table=True, verbose=False):
+    """(dict of result tables with the index reset, list of oi_config dicts) from a results file
+    (local_experts.py:1467-1620); expert-location columns are merged onto every table that holds the coords_col."""
+    if select_tables is not None and add_suffix_to_table:
+        select_tables = [f"{t}{table_suffix}" for t in select_tables]
+    with pd.HDFStore(results_file, mode="r") as store:
+        try:
+            cfg = store.get(f"oi_config{table_suffix}")[["config"]].drop_duplicates()
+            oi_config = [nested_dict_literal_eval(json.loads(c)) for c in cfg["config"].values]
+        except Exception:
+            try:
+                oi_config = [nested_dict_literal_eval(store.get_storer(f"oi_config{table_suffix}").attrs["oi_config"])]
+            except Exception:
+                oi_config = []
+        keys = [re.sub("^/", "", k) for k in store.keys()]
+        wanted = keys if select_tables is None else select_tables
+        dfs = {}
+        for k in keys:
+            if k in wanted:
                 try:
-                    if k.startswith("oi_config"):
-                        store.append(key=k, value=v, min_itemsize={"config": 65536}, data_columns=["idx"])
-                    elif k.startswith("expert_locs"):
-                        store.append(key=k, value=v, data_columns=True)
-                    else:
-                        store.append(key=k, value=v, min_itemsize=min_itemsize)
-                except ValueError as e:
-                    print(e)
+                    dfs[k] = store.select(k).reset_index()
+                except Exception as e:
+                    print(f"issue with key: {k}\n{e}")
+    if global_col_funcs is not None:
+        for k in dfs:
+            try:
+                dl.add_cols(dfs[k], global_col_funcs)
+            except Exception as e:
+                print(f"Adding/Modifying columns had Exception:{e}\non key/table: {k}")
+    expert_locations = None
+    if f"expert_locs{table_suffix}" in dfs:
+        expert_locations = dfs[f"expert_locs{table_suffix}"].copy(True)
+    else:
+        try:
+            expert_locations = pd.concat([LocalExpertOI(expert_loc_config=c["locations"]).expert_locs.copy(True)
+                                          for c in oi_config])
+        except Exception as e:
+            print(f"in get_results_from_h5file trying read expert_locations from file got Exception:\n{e}")
+    if expert_locations is not None and merge_on_expert_locations:
+        try:
+            coords_col = oi_config[0]["data"]["coords_col"]
+        except KeyError:
+            coords_col = oi_config[0]["input_data"]["coords_col"]
+        for k in dfs:
+            if np.isin(coords_col, dfs[k].columns).all():
+                dfs[k] = dfs[k].merge(expert_locations, on=coords_col, how="left", suffixes=["", "_expert_location"])
+    return dfs, oi_config
 
 
 def get_results_from_tables(tables, table_suffix=""):
-    """Convenience: strip the suffix so callers can index tables like the reference's
-    get_results_from_h5file output (local_experts.py:1467-1620)."""
+    """Tables returned by ``run(return_tables=True)`` with the suffix stripped from their names."""
     return {re.sub(f"{re.escape(table_suffix)}$", "", k): v for k, v in tables.items()}

@@ -197,6 +197,12 @@ def main():
     oi.run(store_path=store_path, **rk)
     tabs = dump_store(store_path, "scenario_a")
     print({k: len(v["data"][v["columns"][0]]["values"]) for k, v in tabs.items()})
+    # the reference's reader of that file (local_experts.py:1467-1620)
+    from GPSat.local_experts import get_results_from_h5file
+    dfs, oi_cfg = get_results_from_h5file(store_path)
+    with open(os.path.join(OUT, "results_a.json"), "w") as f:
+        json.dump({"tables": {k: frame_to_json(v) for k, v in dfs.items()}, "n_config": len(oi_cfg),
+                   "config_keys": sorted(oi_cfg[0].keys())}, f)
 
     # ---- scenario B: "smoothed" parameter tables in the same file, predict-only (the example's second config) ----
     with pd.HDFStore(store_path, mode="a") as st:

@@ -1,5 +1,5 @@
-"""world_size-2 gloo tests (CPU) of the multi-GPU host logic: LPT partition, ragged gather and the merge
-back into global expert order.  No GPU and no engine: every rank fabricates its shard's results from a
+"""world_size-2 gloo tests (CPU) of the multi-GPU host logic: LPT partition, the packed single-payload gather
+(pack -> all_gather -> unpack) and the merge back into global expert order.  No GPU and no engine: every rank fabricates its shard's results from a
 deterministic function of the global expert index, the merged result must equal the single-process one."""
 import os
 import socket
@@ -10,7 +10,7 @@ import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
-from gpsat_b200.distributed import _gather_padded, merge_shards, partition_lpt
+from gpsat_b200.distributed import gather_results, merge_shards, pack_results, partition_lpt, unpack_results
 
 
 def test_partition_lpt_balances_and_is_deterministic():
@@ -41,7 +41,12 @@ def _fake_result(gidx, D=3):
     poff[1:] = np.cumsum(cnt)
     rep = np.repeat(g, cnt)
     within = np.concatenate([np.arange(c) for c in cnt]) if len(cnt) else np.zeros(0, dtype=np.int64)
-    return dict(num_obs=num_obs, has_pred=has_pred, too_few=too_few, valid=valid, valid_idx=vidx, n_valid=len(vidx),
+    zcnt = 2 + (g % 3)
+    zoff = np.zeros(len(g) + 1, dtype=np.int64)
+    zoff[1:] = np.cumsum(zcnt)
+    zrep = np.repeat(g, zcnt)
+    return dict(z_offsets=zoff, inducing_points=np.stack([zrep * 1.5, zrep - 1.0, zrep * 0.25], axis=1),
+                num_obs=num_obs, has_pred=has_pred, too_few=too_few, valid=valid, valid_idx=vidx, n_valid=len(vidx),
                 theta=np.stack([g + 0.1 * k for k in range(D + 2)], axis=1).astype(float), fobj=-1.0 * g,
                 obs_mean=0.5 * g, status=(g % 3).astype(np.int32), nit=(g % 17).astype(np.int32),
                 nfev=(g % 19).astype(np.int32), pred_offsets=poff,
@@ -57,20 +62,9 @@ def _worker(rank, world, port, E, q):
         cost = ((np.arange(E) * 37) % 101 + 1.0) ** 3
         shards = partition_lpt(cost, world)
         res = _fake_result(shards[rank])
-        keys = [k for k in res if k != "n_valid"]
-        gathered = {}
-        for k in keys:
-            t = torch.as_tensor(np.ascontiguousarray(res[k]))
-            if t.dtype == torch.bool:
-                t = t.to(torch.uint8)
-            gathered[k] = [g.numpy() for g in _gather_padded(t)]
-        parts = []
-        for r in range(world):
-            p = {k: gathered[k][r] for k in keys}
-            for k in ("has_pred", "too_few", "valid"):
-                p[k] = p[k].astype(bool)
-            p["n_valid"] = int(p["valid"].sum())
-            parts.append(p)
+        # the engine hands back device tensors; here they are CPU tensors and the collective runs over gloo
+        rt = {k: (torch.as_tensor(np.ascontiguousarray(v)) if isinstance(v, np.ndarray) else v) for k, v in res.items()}
+        parts = gather_results(rt, 3, torch.device("cpu"))
         merged = merge_shards(shards, parts, E)
         if rank == 0:
             q.put({k: (v.tolist() if isinstance(v, np.ndarray) else v) for k, v in merged.items()})
@@ -95,3 +89,15 @@ def test_sharded_gather_matches_single_process(E):
     ref = _fake_result(np.arange(E))
     for k, v in ref.items():
         np.testing.assert_array_equal(np.asarray(merged[k]), np.asarray(v), err_msg=k)
+
+
+def test_pack_unpack_round_trip_including_empty_shards():
+    for gidx in ([], [0], [0, 11, 22], list(range(3, 40))):       # multiples of 11 have no prediction locations
+        res = _fake_result(np.asarray(gidx, dtype=np.int64))
+        rt = {k: (torch.as_tensor(np.ascontiguousarray(v)) if isinstance(v, np.ndarray) else v) for k, v in res.items()}
+        header, payload = pack_results(rt, 3, torch.device("cpu"))
+        back = unpack_results(header.numpy(), payload.numpy(), 3)
+        for k, v in res.items():
+            if res["n_valid"] == 0 and k not in ("num_obs", "has_pred", "too_few", "valid", "n_valid", "valid_idx"):
+                continue
+            np.testing.assert_array_equal(np.asarray(back[k]).reshape(np.asarray(v).shape), np.asarray(v), err_msg=k)

@@ -127,8 +127,9 @@ def test_randomised_dimensions_kernels_sizes(eng, D):
             np.testing.assert_allclose(g[e], gr, rtol=1e-7, atol=1e-7 * max(np.abs(gr).max(), 1.0),
                                        err_msg=f"{kernel} n={n}")
             m, v, _ = gpr.predict(Xs[e] / cs, y, Xp / cs, theta[e, :D], theta[e, D], theta[e, D + 1], kernel)
-            np.testing.assert_allclose(fm[e], m, rtol=1e-7, atol=1e-9, err_msg=f"{kernel} n={n}")
-            np.testing.assert_allclose(fv[e], v, rtol=1e-6, atol=1e-10, err_msg=f"{kernel} n={n}")
+            np.testing.assert_allclose(fm[e], m, rtol=RTOL_FIXED, atol=RTOL_FIXED * np.abs(m).max(),
+                                       err_msg=f"{kernel} n={n}")
+            np.testing.assert_allclose(fv[e], v, rtol=RTOL_FIXED, atol=1e-12, err_msg=f"{kernel} n={n}")
 
 
 
@@ -418,7 +419,11 @@ def test_bucketed_selection_bit_exact(eng, golden_dir):
 # ---------------------------------------------------------------------------------------------
 # full-size experts (BASELINE configs 3 / 4: N ~ 2k and beyond) and failure handling
 # ---------------------------------------------------------------------------------------------
-def test_large_experts_objective_gradient_predict(eng):
+def test_large_experts_objective_gradient_predict(eng, golden_dir):
+    """N = 2100 / 4300 at fixed hyper-parameters: 1e-8 against the float64 oracle AND against the extended-precision
+    (80-bit long double) evaluation of the same formulas (tests/golden/extended.npz, make_golden_extended.py), which
+    shows both float64 implementations sit ~1e-13 from the true value at this size."""
+    ext = _load(golden_dir, "extended.npz")
     rng = np.random.default_rng(41)
     sizes = [2100, 4300]
     Xs, zs = [], []
@@ -441,10 +446,14 @@ def test_large_experts_objective_gradient_predict(eng):
     for e in range(2):
         fr, gr = gpr.neg_lml_and_grad(Xs[e] / cs, zs[e], theta[e, :3], theta[e, 3], theta[e, 4])
         assert abs(f[e] - fr) <= RTOL_FIXED * abs(fr)
-        np.testing.assert_allclose(g[e], gr, rtol=1e-6, atol=1e-6 * np.abs(gr).max())
+        np.testing.assert_allclose(g[e], gr, rtol=RTOL_FIXED, atol=RTOL_FIXED * np.abs(gr).max())
         m, v, _ = gpr.predict(Xs[e] / cs, zs[e], Xp / cs, theta[e, :3], theta[e, 3], theta[e, 4])
-        np.testing.assert_allclose(fm[e * P:(e + 1) * P], m, rtol=1e-7, atol=1e-10)
-        np.testing.assert_allclose(fv[e * P:(e + 1) * P], v, rtol=1e-6, atol=1e-10)
+        n = sizes[e]
+        assert abs(f[e] - ext[f"f_{n}"]) <= RTOL_FIXED * abs(ext[f"f_{n}"])
+        for ref_m, ref_v in ((m, v), (ext[f"mean_{n}"], ext[f"fvar_{n}"])):
+            np.testing.assert_allclose(fm[e * P:(e + 1) * P], ref_m, rtol=RTOL_FIXED,
+                                       atol=RTOL_FIXED * np.abs(ref_m).max())
+            np.testing.assert_allclose(fv[e * P:(e + 1) * P], ref_v, rtol=RTOL_FIXED, atol=1e-14)
 
 
 def test_c4_size_expert_8000_obs(eng):
@@ -485,8 +494,8 @@ def test_c4_size_expert_8000_obs(eng):
     Xp = np.column_stack([rng.uniform(-2e5, 2e5, (P, 2)), np.full(P, 18326.0)])
     fmean, fvar, _, _ = eng.predict(b, theta, np.array([0, P, P]), Xp)
     m, v, _ = gpr.predict(Xs[0] / cs, zs[0], Xp / cs, theta[0, :3], theta[0, 3], theta[0, 4])
-    np.testing.assert_allclose(fmean.cpu().numpy(), m, rtol=1e-7, atol=1e-10)
-    np.testing.assert_allclose(fvar.cpu().numpy(), v, rtol=1e-6, atol=1e-10)
+    np.testing.assert_allclose(fmean.cpu().numpy(), m, rtol=RTOL_FIXED, atol=RTOL_FIXED * np.abs(m).max())
+    np.testing.assert_allclose(fvar.cpu().numpy(), v, rtol=RTOL_FIXED, atol=1e-14)
 
 
 def test_c3_size_optimise_properties(eng):

@@ -5,7 +5,8 @@ import pandas as pd
 import pytest
 
 from gpsat_b200.batched import ModelSpec, sel_terms
-from gpsat_b200.local_experts import _apply_where, _where_list, pretty_print_class
+from gpsat_b200.dataloader import data_select, get_where_list
+from gpsat_b200.local_experts import pretty_print_class
 from gpsat_b200.model import B200GPRModel, get_model
 from gpsat_b200.params import HyperParams
 from oracle import gpr
@@ -98,11 +99,51 @@ def test_sel_terms_and_where_list():
     assert t[0]["cols"] == [2] and t[2]["cols"] == [0, 1] and t[2]["val"] == 300_000
     gs = [{"col": "lat", "comp": ">=", "val": 60},
           {"loc_col": "t", "src_col": "date", "func": "lambda x,y: np.datetime64(pd.to_datetime(x+y, unit='D'))"}]
-    w = _where_list(gs, ls, {"x": 0.0, "y": 0.0, "t": 18326.0})
+    w = get_where_list(gs, ls, {"x": 0.0, "y": 0.0, "t": 18326.0})
     assert w[0] == gs[0]
     assert w[1] == {"col": "date", "comp": "<=", "val": np.datetime64("2020-03-09")}
     assert w[2] == {"col": "date", "comp": ">=", "val": np.datetime64("2020-03-01")}
     df = pd.DataFrame({"lat": [50.0, 70.0, 80.0],
                        "date": pd.to_datetime(["2020-03-05", "2020-03-05", "2020-04-01"])})
-    assert _apply_where(df, w).index.tolist() == [1]
+    assert data_select(df, where=w).index.tolist() == [1]
     assert pretty_print_class(B200GPRModel) == "gpsat_b200.model.B200GPRModel"
+
+
+def test_register_wraps_get_model_in_all_three_namespaces():
+    """GPSat.models.get_model is imported by value into GPSat.local_experts and GPSat.postprocessing
+    (models/__init__.py:3, local_experts.py:32, postprocessing.py:18): register() must wrap all three."""
+    import sys
+    import types
+    from gpsat_b200 import model as bm
+
+    def ref_get_model(name):
+        if name == "sklearnGPRModel":
+            return "sk"
+        raise NotImplementedError(f"model with name: '{name}' is not implemented")
+
+    saved = {k: sys.modules.get(k) for k in ("GPSat", "GPSat.models", "GPSat.local_experts", "GPSat.postprocessing")}
+    try:
+        pkg = types.ModuleType("GPSat")
+        sys.modules["GPSat"] = pkg
+        mods = []
+        for nm in ("models", "local_experts", "postprocessing"):
+            m = types.ModuleType(f"GPSat.{nm}")
+            m.get_model = ref_get_model
+            sys.modules[f"GPSat.{nm}"] = m
+            setattr(pkg, nm, m)
+            mods.append(m)
+        bm.register()
+        for m in mods:
+            assert m.get_model("B200GPRModel") is bm.B200GPRModel
+            assert m.get_model("B200SGPRModel") is bm.B200SGPRModel
+            assert m.get_model("sklearnGPRModel") == "sk"          # everything else still goes to the reference
+            with pytest.raises(NotImplementedError):
+                m.get_model("nope")
+        bm.register()                                               # idempotent
+        assert mods[0].get_model("B200GPRModel") is bm.B200GPRModel
+    finally:
+        for k, v in saved.items():
+            if v is None:
+                sys.modules.pop(k, None)
+            else:
+                sys.modules[k] = v
