@@ -6,8 +6,10 @@
 
 A "step" is one pass of the hot path (prediction-location filter -> observation selection ->
 gather -> L-BFGS optimisation of every expert -> objective -> predictive mean / variance) over one
-batch of experts of the named workload.  Experts are independent, so ranks take disjoint batches
-(weak scaling, no data-path collective); the only collective is the timing reduction.
+LIST of experts of the named workload.  With N GPUs the list holds N x --experts-per-step experts and goes through
+gpsat_b200.distributed.run_experts_sharded: every rank derives the same LPT partition by N^3 cost, runs its shard,
+and ONE packed all_gather returns the results to every rank (weak scaling: per-GPU work is fixed as N grows; at
+N = 8 the default list is the whole 8192-expert lattice).  --strong fixes the list at --total-experts instead.
 """
 from __future__ import annotations
 
@@ -25,17 +27,21 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
-# per-launch DRAM traffic (bytes) of the dominant kernel of each phase, from the committed ncu --set full captures
-# (profiles/*_summary.md); filled in when a capture of the current kernel generation exists
-TRAFFIC = {
-    # k_potrf_panel, panel J = 4 of 17 (2561 CTAs, 197 slots, N ~ 2.1k) from the ncu --set full capture
-    # profiles/r01f_summary.md: 1.64 GB read + 0.31 GB written per launch.  Algorithmic bytes of that launch (every
-    # CTA reads its L row panel and the L column panel once, the K tiles once, and writes its L tiles): 2.6 GB, i.e.
-    # L2 already absorbs part of the operand re-reads (26 % sector hit rate)
-    "potrf": 1.951e9,
-    "trtri": 2.595e9,     # k_trtri_pass1, level h = 8 (64 x 197 CTAs), profiles/r01f_busy.md
-    "lauum": 3.995e9,     # k_lauum2 (120 x 197 CTAs), profiles/r01f_busy.md
-}
+# per-launch DRAM traffic (bytes) of each phase's dominant kernel comes from profiles/r02_traffic.json, written by
+# profiles/capture_traffic.sh from an `ncu --set full` capture of THIS command line's batch configuration; when the
+# file is missing or was captured for another experts-per-step the key is null (a number from another batch size
+# says nothing about this run)
+def load_traffic(experts_per_step, workload):
+    path = os.path.join(ROOT, "profiles", "r02_traffic.json")
+    try:
+        with open(path) as f:
+            t = json.load(f)
+        if t.get("experts_per_step") == experts_per_step and t.get("workload") == workload:
+            return t
+    except (OSError, ValueError):
+        pass
+    return None
+
 
 METRIC = "experts/sec (optimise+predict)"
 UNIT = "experts/s"
@@ -49,9 +55,12 @@ def parse():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="c3", choices=["c3", "c1", "c2", "c4", "c5", "tiny"])
     ap.add_argument("--experts-per-step", type=int, default=1024, help="experts per rank per step")
-    ap.add_argument("--cpu-sample", type=int, default=3,
-                    help="experts timed by the cpu_baseline leg / per step of --impl reference (~6 s each)")
+    ap.add_argument("--cpu-sample", type=int, default=32,
+                    help="experts of the fixed CPU sample (the first K of the fixed-seed expert order): timed by the "
+                         "cpu_baseline leg, and spread over the steps of --impl reference")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--strong", action="store_true", help="one fixed list of --total-experts for every N")
+    ap.add_argument("--total-experts", type=int, default=8192)
     return ap.parse_args()
 
 
@@ -128,20 +137,37 @@ def cpu_experts_per_sec(w, expert_rows, n_threads_note=True):
     return len(per) / dt, dt, per
 
 
+def cpu_cores():
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
+def use_all_cores():
+    """torch.distributed.run exports OMP_NUM_THREADS=1; the CPU arm must not be measured on one thread"""
+    n = cpu_cores()
+    try:
+        from threadpoolctl import threadpool_limits
+        threadpool_limits(limits=n)
+    except Exception:
+        pass
+    return n
+
+
 def cpu_threads():
     try:
         from threadpoolctl import threadpool_info
         n = max([p.get("num_threads", 1) for p in threadpool_info()] or [1])
     except Exception:
-        n = os.cpu_count() or 1
+        n = cpu_cores()
     return int(n)
 
 
-def median_experts(w, k):
-    """k experts around the middle of the list (representative N)."""
-    E = len(w["experts"])
-    lo = max(0, E // 2 - k // 2)
-    return w["experts"][lo:lo + k]
+def expert_order(w):
+    """the fixed-seed order both arms draw their experts from (batches are statistically identical samples of the
+    density-varying lattice; the CPU sample is its first K entries)"""
+    return np.random.default_rng(12345).permutation(len(w["experts"]))
 
 
 def run_reference(args):
@@ -150,24 +176,27 @@ def run_reference(args):
         return
     from gpsat_b200 import synthetic
     w = synthetic.workload(args.workload)
-    k = max(1, args.cpu_sample)
+    cores = use_all_cores()
+    order = expert_order(w)
+    k = max(1, -(-args.cpu_sample // max(args.steps, 1)))       # ceil: the steps together cover >= cpu_sample experts
     for _ in range(min(args.warmup, 1)):         # BLAS thread pools / imports
-        cpu_experts_per_sec(w, median_experts(w, 1))
-    vals, secs = [], 0.0
+        cpu_experts_per_sec(w, w["experts"][order[-1:]])
+    n, secs = 0, 0.0
     for s in range(args.steps):
-        lo = (len(w["experts"]) // 2 + s * k) % (len(w["experts"]) - k)
-        v, dt, _ = cpu_experts_per_sec(w, w["experts"][lo:lo + k])
-        vals.append(k)
+        idx = order[(s * k) % len(order):(s * k) % len(order) + k]
+        v, dt, per = cpu_experts_per_sec(w, w["experts"][idx])
+        n += len(per)
         secs += dt
-    value = sum(vals) / secs
+    value = n / secs
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * secs / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": f"{w['name']}: {w['describe']}", "experts_per_step": k},
-            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cpu_threads(), "kind": "port",
-                             "sample": f"{k} expert(s) per step x {args.steps} steps from the middle of the "
-                                       f"{w['name']} expert list; sequential oracle loop (numpy/LAPACK + scipy "
-                                       "L-BFGS-B); the reference's GPflow/TensorFlow stack is not installable here"},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "threads": cpu_threads(), "kind": "port",
+                             "sample": f"the first {n} experts of the fixed-seed {w['name']} expert order ({k} per step "
+                                       f"x {args.steps} steps); sequential oracle loop (numpy/LAPACK + scipy "
+                                       "L-BFGS-B) on all host cores; the reference's GPflow/TensorFlow stack is not "
+                                       "installable here"},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line), flush=True)
@@ -186,32 +215,27 @@ def run_b200(args):
     torch.cuda.set_device(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    from gpsat_b200 import build, get_engine, synthetic
+    from gpsat_b200 import build, distributed, get_engine, synthetic
     from gpsat_b200.batched import ModelSpec, run_experts, run_experts_host, h2d_bytes
     build.build()
     eng = get_engine(local)
     dev = eng.device
     w = synthetic.workload(args.workload)
     spec = ModelSpec.from_model_config(w["model"])
-    B = min(args.experts_per_step, len(w["experts"]))
     E_all = len(w["experts"])
-    n_chunks = max(1, E_all // B)
-    # fixed random order: every batch is a statistically identical sample of the lattice, so per-GPU work
-    # does not depend on which part of the (density-varying) domain a rank happens to get
-    experts_perm = w["experts"][np.random.default_rng(12345).permutation(E_all)]
-
-    perm = np.random.default_rng(12345).permutation(E_all)
+    order = expert_order(w)
+    if args.strong:
+        L = min(args.total_experts, E_all)              # one fixed list for every N
+        B = -(-L // world)
+    else:
+        B = min(args.experts_per_step, E_all)           # per GPU
+        L = min(B * world, E_all)
     theta_all = w.get("theta")          # predict-only workloads: per-expert hyper-parameters to load
 
-    def chunk(step):
-        c = (step * world + rank) % n_chunks
-        return np.ascontiguousarray(experts_perm[c * B:(c + 1) * B])
-
-    def chunk_theta(step):
-        if theta_all is None:
-            return None
-        c = (step * world + rank) % n_chunks
-        return np.ascontiguousarray(theta_all[perm[c * B:(c + 1) * B]])
+    def list_idx(step):
+        """the step's expert list: the next L entries of the fixed-seed order (wrapping around the lattice)"""
+        lo = (step * L) % E_all
+        return np.r_[order[lo:lo + L], order[:max(0, lo + L - E_all)]]
 
     table_h = torch.from_numpy(w["table"]).pin_memory()
     pred_h = torch.from_numpy(w["pred"]).pin_memory()
@@ -219,29 +243,48 @@ def run_b200(args):
     kw = dict(table_cols=w["table_cols"], obs_col=w["obs_col"], coords_col=w["coords_col"],
               ref_cols=w["expert_cols"], local_select=w["local_select"], pred_cols=w["pred_cols"],
               max_dist=w["max_dist"], optimise=w["optimise"])
+    shard_stats = []
 
     def step_device(step):
-        refs = torch.from_numpy(chunk(step)).to(dev)
-        return run_experts(eng, spec, table_d, refs_dev=refs, pred_table_dev=pred_d, theta_init=chunk_theta(step), **kw)
+        """inputs resident in HBM: the observation / prediction tables stay on the device, only the step's expert
+        rows (KBs) are new.  N > 1: LPT shard + the single packed result gather are inside the step."""
+        idx = list_idx(step)
+        th = None if theta_all is None else np.ascontiguousarray(theta_all[idx])
+        if world == 1:
+            refs = torch.from_numpy(np.ascontiguousarray(w["experts"][idx])).to(dev)
+            return run_experts(eng, spec, table_d, refs_dev=refs, pred_table_dev=pred_d, theta_init=th, **kw)
+        r = distributed.run_experts_sharded(eng, spec, table_d, experts=w["experts"][idx], pred_table=pred_d,
+                                            theta_init=th, **kw)
+        shard_stats.append(dict(distributed.LAST))
+        return r
+
+    def step_host(step):
+        """end to end through the host-buffer API: tables from pinned host memory, results back as numpy"""
+        idx = list_idx(step)
+        th = None if theta_all is None else np.ascontiguousarray(theta_all[idx])
+        if world == 1:
+            return run_experts_host(eng, spec, table_h, experts=w["experts"][idx], pred_table=pred_h, theta_init=th,
+                                    **kw)
+        return distributed.run_experts_sharded(eng, spec, table_h, experts=w["experts"][idx], pred_table=pred_h,
+                                               theta_init=th, **kw)
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    def maxreduce(x):
+    def reduce(x, op):
         if world == 1:
             return x
         t = torch.tensor([x], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(t, op=op)
         return float(t.item())
 
-    def sumreduce(x):
-        if world == 1:
-            return x
-        t = torch.tensor([x], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.SUM)
-        return float(t.item())
+    maxreduce = lambda x: reduce(x, dist.ReduceOp.MAX)
+    sumreduce = lambda x: reduce(x, dist.ReduceOp.SUM)
+
+    def scalar(v):
+        return float(v.float().mean().item()) if isinstance(v, torch.Tensor) else float(np.mean(v))
 
     # FP64 roofline denominators measured on this GPU before the run
     dmma_peak = eng.dmma_peak_tflops()
@@ -261,33 +304,58 @@ def run_b200(args):
     # ---- device-resident timing ----
     for s in range(args.warmup):
         step_device(s)
+    shard_stats.clear()
     sampler = ClockSampler(local)
     barrier()
     if rank == 0:
         sampler.start()
     l0 = eng.launch_count()
     ev0, ev1 = torch.cuda.Event(True), torch.cuda.Event(True)
+    t0 = time.perf_counter()
     ev0.record()
     n_done, nfev_sum, nobs, nfev_max = 0, 0, [], 0
     for s in range(args.steps):
         r = step_device(args.warmup + s)
-        n_done += r["n_valid"]
-        nfev_sum += int(r["nfev"].sum().item()) if "nfev" in r else 0
-        nfev_max = max(nfev_max, int(r["nfev"].max().item()) if "nfev" in r else 0)
-        nobs.append(r["num_obs"].float().mean().item())
+        n_done += int(r["n_valid"])
+        if "nfev" in r:
+            nf = r["nfev"]
+            nfev_sum += int(nf.sum())
+            nfev_max = max(nfev_max, int(nf.max()))
+        nobs.append(scalar(r["num_obs"]))
     ev1.record()
     barrier()
-    ms = maxreduce(ev0.elapsed_time(ev1))
+    # device events on this rank's stream, max over ranks; the sharded step ends with host work (merge), so the
+    # wall clock is taken too and the larger of the two counts
+    ms = max(maxreduce(ev0.elapsed_time(ev1)), maxreduce((time.perf_counter() - t0) * 1e3) if world > 1 else 0.0)
     clocks = sampler.stop() if rank == 0 else None
     launches = eng.launch_count() - l0
-    total_experts = sumreduce(float(n_done))
+    total_experts = float(n_done) if world > 1 else float(n_done)     # sharded results are already global
     value = total_experts / (ms * 1e-3)
+    sharding = None
+    if world > 1:
+        comp = np.array([s_["compute_s"] for s_ in shard_stats])
+        gath = np.array([s_["gather_s"] for s_ in shard_stats])
+        cost = shard_stats[-1]["shard_cost"]
+        sharding = {"mode": ("strong: one fixed list of %d experts" % L) if args.strong else
+                            ("one list of %d x %d experts per step" % (world, B)),
+                    "partition": "LPT greedy on N^3 (identical on every rank, no communication)",
+                    "collective": "one packed all_gather of the per-expert / per-prediction results per step (NCCL)",
+                    "shard_compute_ms_per_step_max": maxreduce(float(comp.mean() * 1e3)),
+                    "shard_compute_ms_per_step_mean": sumreduce(float(comp.mean() * 1e3)) / world,
+                    "gather_and_wait_ms_per_step_rank0": float(gath.mean() * 1e3),
+                    "gather_ms_per_step_min_over_ranks": -maxreduce(-float(gath.mean() * 1e3)),
+                    "cost_imbalance_max_over_mean": maxreduce(cost) / (sumreduce(cost) / world)}
+        sharding["time_imbalance_max_over_mean"] = (sharding["shard_compute_ms_per_step_max"] /
+                                                    sharding["shard_compute_ms_per_step_mean"])
 
     # ---- one more step with per-phase CUDA events (single stream, so the phases do not overlap) ----
     eng.set_profiling(True)
     pe0, pe1 = torch.cuda.Event(True), torch.cuda.Event(True)
     pe0.record()
-    step_device(args.warmup + args.steps - 1)
+    idx = list_idx(args.warmup + args.steps - 1)[rank::world][:B]
+    run_experts(eng, spec, table_d, refs_dev=torch.from_numpy(np.ascontiguousarray(w["experts"][idx])).to(dev),
+                pred_table_dev=pred_d, theta_init=None if theta_all is None else np.ascontiguousarray(theta_all[idx]),
+                **kw)
     pe1.record()
     torch.cuda.synchronize()
     ms_prof = pe0.elapsed_time(pe1)
@@ -295,24 +363,20 @@ def run_b200(args):
     eng.set_profiling(False)
 
     # ---- end to end through the host-buffer API ----
-    refs_h = [torch.from_numpy(chunk(args.warmup + args.steps + s)).pin_memory() for s in range(args.steps)]
-    th_h = [chunk_theta(args.warmup + args.steps + s) for s in range(args.steps)]
-    run_experts_host(eng, spec, table_h, experts=refs_h[0], pred_table=pred_h, theta_init=th_h[0], **kw)
+    step_host(args.warmup + args.steps)
     barrier()
     t0 = time.perf_counter()
     ev0.record()
     n_e2e, d2h = 0, 0
     for s in range(args.steps):
-        r = run_experts_host(eng, spec, table_h, experts=refs_h[s], pred_table=pred_h, theta_init=th_h[s], **kw)
-        n_e2e += r["n_valid"]
+        r = step_host(args.warmup + args.steps + 1 + s)
+        n_e2e += int(r["n_valid"])
         d2h = sum(v.nbytes for v in r.values() if isinstance(v, np.ndarray))
     ev1.record()
     barrier()
-    ms_e2e = maxreduce(ev0.elapsed_time(ev1))
-    wall_e2e = maxreduce((time.perf_counter() - t0) * 1e3)
-    ms_e2e = max(ms_e2e, wall_e2e)
-    e2e_value = sumreduce(float(n_e2e)) / (ms_e2e * 1e-3)
-    h2d = h2d_bytes(table_h, pred_h, refs_h[0])
+    ms_e2e = max(maxreduce(ev0.elapsed_time(ev1)), maxreduce((time.perf_counter() - t0) * 1e3))
+    e2e_value = float(n_e2e) / (ms_e2e * 1e-3)
+    h2d = h2d_bytes(table_h, pred_h) + L * w["experts"].shape[1] * 8
 
     if rank != 0:
         if world > 1:
@@ -328,15 +392,18 @@ def run_b200(args):
         phases[nm] = {"ms": prof[f"ms_{nm}"], "tflops": None}
     dom = max(("potrf", "trtri", "lauum"), key=lambda k: phases[k]["ms"])
     peak = max(dmma_peak, dgemm_peak)
+    traffic = load_traffic(B, w["name"])
     roofline = {"bound": "tensor", "kernel": {"potrf": "k_potrf_panel (batched blocked Cholesky, one launch per panel)",
                                               "trtri": "k_trtri_pass1/2 (triangular inverse)",
                                               "lauum": "k_lauum2 (K^-1 tiles)"}[dom],
                 "achieved": phases[dom]["tflops"], "peak": peak, "unit": "TFLOP/s",
                 "frac": (phases[dom]["tflops"] / peak) if phases[dom]["tflops"] else None,
-                "traffic": TRAFFIC.get(dom),
-                "traffic_note": "dram__bytes_read.sum + dram__bytes_write.sum per launch of the phase's dominant kernel, "
-                                "from the committed ncu --set full capture (profiles/); null when not captured for "
-                                "this kernel generation",
+                "traffic": None if traffic is None else traffic.get(dom, {}).get("dram_bytes_per_launch"),
+                "traffic_note": ("dram__bytes_read.sum + dram__bytes_write.sum per launch of the phase's dominant kernel "
+                                 "from the ncu --set full capture of this batch configuration: " +
+                                 json.dumps(traffic.get(dom))) if traffic else
+                                "null: no ncu --set full capture of this batch configuration is committed "
+                                "(profiles/r02_traffic.json)",
                 "peak_source": f"FP64 measured on this GPU in this run: DMMA register-chain {dmma_peak:.1f} TF, "
                                f"cuBLAS DGEMM 4096^3 {dgemm_peak:.1f} TF (MEASURED_PEAKS.json has no FP64 entry)",
                 "flops_model": "sum over active experts of N^3/3 per phase per objective evaluation",
@@ -347,21 +414,31 @@ def run_b200(args):
 
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
-        k = max(1, args.cpu_sample)
-        v, dt, _ = cpu_experts_per_sec(w, median_experts(w, k))
-        cpu = {"value": v, "unit": UNIT, "cores": cpu_threads(), "kind": "port",
-               "sample": f"{k} expert(s) from the middle of the {w['name']} expert list, sequential oracle loop "
-                         f"(numpy/LAPACK + scipy L-BFGS-B), {dt:.1f} s"}
+        # the same code path, sample and thread count as the --impl reference arm, in its own process (the OpenBLAS
+        # pool of this process shares the cores with torch's threads and the clock sampler)
+        cmd = [sys.executable, os.path.abspath(__file__), "--impl", "reference", "--workload", args.workload,
+               "--steps", "1", "--warmup", "1", "--cpu-sample", str(args.cpu_sample)]
+        env = {k: v for k, v in os.environ.items() if k not in ("OMP_NUM_THREADS", "MKL_NUM_THREADS")}
+        out = subprocess.run(cmd, capture_output=True, text=True, env=env)
+        try:
+            cpu = json.loads(out.stdout.strip().splitlines()[-1])["cpu_baseline"]
+        except Exception:
+            cpu = {"value": None, "unit": UNIT, "cores": cpu_cores(), "kind": "port",
+                   "sample": "cpu_baseline leg failed: " + out.stderr[-300:]}
 
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
+            "scaling": "strong" if args.strong else "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": f"{w['name']}: {w['describe']}", "experts_per_step_per_gpu": B,
-                       "batching": "each step = one batched optimise+predict call over a fixed-seed random "
-                                   f"sample of {B} of the {E_all} lattice experts per GPU",
-                       "mean_obs_per_expert": float(np.mean(nobs)), "mean_nfev": nfev_sum / max(n_done, 1), "max_nfev": nfev_max,
+                       "experts_per_step": L,
+                       "batching": f"each step = ONE list of {L} experts (fixed-seed order over the {E_all} lattice "
+                                   "experts) through one batched optimise+predict call per GPU" +
+                                   ("" if world == 1 else "; the list is LPT-sharded over the ranks and gathered once"),
+                       "mean_obs_per_expert": float(np.mean(nobs)), "mean_nfev": nfev_sum / max(n_done, 1),
+                       "max_nfev": nfev_max, "sharding": sharding,
                        "l2": "inputs larger than L2 (factor workspaces are GBs per step)"},
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": int(d2h)},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
             "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu}
     print(json.dumps(line), flush=True)
     if world > 1:

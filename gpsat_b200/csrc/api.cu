@@ -65,6 +65,8 @@ struct gpsat_handle {
   cudaEvent_t ev_fork = nullptr;
   int groups_ready = 0;
   bool attrs_set = false;
+  int* timeouts_dev = nullptr;   // [1] flag-wait timeouts of k_potrf_panel (device counter, see GPSAT_ESYNC)
+  long long timeouts_seen = 0;   // value already reported to the caller
 };
 
 static int ensure(Buf& b, size_t bytes) {
@@ -128,6 +130,10 @@ extern "C" int gpsat_create(gpsat_handle** out, int device, size_t mem_budget_by
   CK(cudaFuncSetAttribute(k_tgemm<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM2_BYTES));
   CK(cudaFuncSetAttribute(k_tgemm<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM2_BYTES));
   CK(cudaFuncSetAttribute(k_tgemm<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM2_BYTES));
+  // function attributes are per device: set here for this handle's device, not once per process
+  CK(cudaFuncSetAttribute(k_select_bucket, cudaFuncAttributeMaxDynamicSharedMemorySize, 32768 * sizeof(int)));
+  CK(cudaMalloc(&h->timeouts_dev, sizeof(int)));
+  CK(cudaMemset(h->timeouts_dev, 0, sizeof(int)));
   *out = h;
   return 0;
 }
@@ -142,6 +148,7 @@ extern "C" int gpsat_destroy(gpsat_handle* h) {
   for (Buf* b : bs)
     if (b->p) cudaFree(b->p);
   if (h->host_ints) cudaFreeHost(h->host_ints);
+  if (h->timeouts_dev) cudaFree(h->timeouts_dev);
   for (int g = 0; g < h->groups_ready; ++g) { cudaStreamDestroy(h->gstream[g]); cudaEventDestroy(h->gevent[g]); }
   if (h->ev_fork) cudaEventDestroy(h->ev_fork);
   for (auto e : h->ev) cudaEventDestroy(e);
@@ -150,6 +157,24 @@ extern "C" int gpsat_destroy(gpsat_handle* h) {
 }
 
 extern "C" long long gpsat_launch_count(const gpsat_handle* h) { return h ? h->launches : 0; }
+extern "C" long long gpsat_sync_timeouts(gpsat_handle* h) {
+  if (!h || !h->timeouts_dev) return 0;
+  int v = 0;
+  cudaSetDevice(h->device);
+  if (cudaMemcpy(&v, h->timeouts_dev, sizeof(int), cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
+  return v;
+}
+// after a call's final synchronisation: new flag-wait timeouts since the last report -> GPSAT_ESYNC
+static int check_sync_timeouts(gpsat_handle* h) {
+  const long long v = gpsat_sync_timeouts(h);
+  if (v > h->timeouts_seen) {
+    const long long d = v - h->timeouts_seen;
+    h->timeouts_seen = v;
+    return fail(GPSAT_ESYNC, std::to_string(d) + " Cholesky panel CTA(s) timed out waiting for a diagonal block; the "
+                             "affected evaluations were treated as non-positive-definite (f = +inf)");
+  }
+  return 0;
+}
 extern "C" int gpsat_set_profiling(gpsat_handle* h, int enabled) {
   if (!h) return GPSAT_EINVAL;
   h->profiling = enabled != 0;
@@ -268,6 +293,7 @@ static int setup_work(gpsat_handle* h, const gpsat_batch* b, const Plan& pl, Wor
   c.n = ip; c.nb = ip + S; c.active = ip + 2 * S; c.fail = ip + 3 * S; c.pflag = ip + 6 * S;
   c.theta = (double*)h->theta.p; c.logdet_part = (double*)h->logdet.p; c.gpart = (double*)h->gpart.p;
   c.fout = (double*)h->fout.p; c.gout = (double*)h->gout.p;
+  c.timeouts = h->timeouts_dev;
   w.a.slot_expert = ip + 4 * S;
   w.a.queue_head = ip + 5 * S;
   w.a.states = (LbfgsState*)h->states.p;
@@ -420,7 +446,7 @@ extern "C" int gpsat_gpr_eval(gpsat_handle* h, const gpsat_batch* b, const doubl
   CK(cudaStreamSynchronize(st));
   harvest_profile(h, grad, grad);
   CK(cudaGetLastError());
-  return 0;
+  return check_sync_timeouts(h);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -553,7 +579,10 @@ extern "C" int gpsat_gpr_optimise(gpsat_handle* h, const gpsat_batch* b, const d
   if (trace) fclose(trace);
   harvest_profile(h, true, true);
   CK(cudaGetLastError());
-  return 0;
+  if (live > 0)
+    return fail(GPSAT_ELIMIT, "optimiser round limit reached with " + std::to_string(live) +
+                              " slot group(s) still running: unfinished experts keep status 0");
+  return check_sync_timeouts(h);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -642,7 +671,7 @@ extern "C" int gpsat_gpr_predict(gpsat_handle* h, const gpsat_batch* b, const do
   CK(cudaStreamSynchronize(st));
   harvest_profile(h, true, false);
   CK(cudaGetLastError());
-  return 0;
+  return check_sync_timeouts(h);
 }
 
 // full_cov=True branch of predict (gpflow_models.py:245-263) for ONE expert (the first of the batch)
@@ -832,10 +861,15 @@ extern "C" int gpsat_select_bucket(const gpsat_sel_spec* spec, const gpsat_cell_
   memcpy(&sp, spec, sizeof(sp));
   CellGrid g = make_grid(spec, term, cg);
   const size_t smem = fill ? (size_t)cap * sizeof(int) : 0;
-  static bool attr = false;
-  if (!attr) {
-    CK(cudaFuncSetAttribute(k_select_bucket, cudaFuncAttributeMaxDynamicSharedMemorySize, 32768 * sizeof(int)));
-    attr = true;
+  // (the dynamic shared-memory attribute of k_select_bucket is set per device in gpsat_create; a caller that
+  //  uses the selection entry points without a handle on this device gets it set here)
+  {
+    int dev = 0;
+    static bool attr_dev[64] = {};
+    if (cudaGetDevice(&dev) == cudaSuccess && dev >= 0 && dev < 64 && !attr_dev[dev]) {
+      CK(cudaFuncSetAttribute(k_select_bucket, cudaFuncAttributeMaxDynamicSharedMemorySize, 32768 * sizeof(int)));
+      attr_dev[dev] = true;
+    }
   }
   k_select_bucket<<<n_experts, 256, smem, (cudaStream_t)stream>>>(sp, g, table_dev, (long)n, refs_dev, nrefcols,
                                                                   start_dev, order_dev, fill, cap, counts_dev,

@@ -53,6 +53,7 @@ struct SlotCtx {
   int* pflag;               // [S] k_potrf_panel: J + 1 once the diagonal block of panel J is published (k_quad resets)
   double* fout;             // [S]  -LML
   double* gout;             // [S][MAXP] d(-LML)/dtheta (constrained parameters)
+  int* timeouts;            // [1] device counter of flag-wait timeouts (handle level; reported as GPSAT_ESYNC)
 };
 
 __device__ __forceinline__ double* tile_ptr(double* base, int i, int j) {
@@ -440,7 +441,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_potrf_panel(SlotCtx c, int J, i
       while (ld_acquire_gpu(c.pflag + s) != J + 1) {
         __nanosleep(200);
         if (++spins > 4000000) {
-          c.fail[s] = 1;
+          c.fail[s] = 1;                                  // the evaluation is unusable: f = +inf for this slot ...
+          if (c.timeouts) atomicAdd(c.timeouts, 1);       // ... and the call reports GPSAT_ESYNC, not "non-PD"
           break;
         }
       }

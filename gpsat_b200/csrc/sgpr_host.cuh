@@ -176,7 +176,7 @@ extern "C" int gpsat_sgpr_eval(gpsat_handle* h, const gpsat_sgpr_batch* sb, cons
   }
   CK(cudaStreamSynchronize(st));
   CK(cudaGetLastError());
-  return 0;
+  return check_sync_timeouts(h);
 }
 
 extern "C" int gpsat_sgpr_optimise(gpsat_handle* h, const gpsat_sgpr_batch* sb, const double* theta0_dev,
@@ -218,12 +218,13 @@ extern "C" int gpsat_sgpr_optimise(gpsat_handle* h, const gpsat_sgpr_batch* sb, 
   ++h->launches;
   CK(cudaMemcpyAsync(W.w.a.queue_head, &count, sizeof(int), cudaMemcpyHostToDevice, st));
   const long long max_rounds = (long long)(b->n_experts / S + 2) * (od.maxfun + od.maxls + 2);
+  bool finished = false;
   for (long long round = 0; round < max_rounds; ++round) {
     CK(cudaMemcpyAsync(h->host_ints, W.w.c.n, (size_t)3 * S * sizeof(int), cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
     int nact = 0;
     for (int s = 0; s < S; ++s) nact += h->host_ints[2 * S + s] ? 1 : 0;
-    if (nact == 0) break;
+    if (nact == 0) { finished = true; break; }
     r = sg_round(h, W, true, false, st);
     if (r) return r;
     k_opt_step<<<S, NTHREADS, 0, st>>>(W.w.c, W.w.a, bi, tr, lo, out);
@@ -231,7 +232,9 @@ extern "C" int gpsat_sgpr_optimise(gpsat_handle* h, const gpsat_sgpr_batch* sb, 
   }
   CK(cudaStreamSynchronize(st));
   CK(cudaGetLastError());
-  return 0;
+  if (!finished)
+    return fail(GPSAT_ELIMIT, "optimiser round limit reached with experts still running (status 0)");
+  return check_sync_timeouts(h);
 }
 
 // grid (S): ceil(P/64) per slot
@@ -283,5 +286,5 @@ extern "C" int gpsat_sgpr_predict(gpsat_handle* h, const gpsat_sgpr_batch* sb, c
   }
   CK(cudaStreamSynchronize(st));
   CK(cudaGetLastError());
-  return 0;
+  return check_sync_timeouts(h);
 }

@@ -32,6 +32,10 @@ extern "C" {
 #define GPSAT_EINVAL (-1)   /* bad argument */
 #define GPSAT_ENOMEM (-2)   /* workspace does not fit the memory budget */
 #define GPSAT_ENOGPU (-3)   /* no CUDA device / wrong architecture */
+#define GPSAT_ELIMIT (-4)   /* the optimiser's round limit was reached with experts still running (status 0) */
+#define GPSAT_ESYNC (-5)    /* a Cholesky panel CTA timed out waiting for its slot's diagonal block (lost
+                               inter-CTA flag): the affected evaluations were treated as f = +inf; results of the
+                               call are complete but must not be trusted silently */
 
 /* kernel ids: gpflow.kernels.{Matern32, Matern52, Matern12|Exponential, SquaredExponential|RBF}
  * (gpflow_models.py:116-135) */
@@ -211,6 +215,8 @@ int gpsat_debug_factor(gpsat_handle* h, const gpsat_batch* b, const double* thet
  * potrf = k_potrf_* + k_quad (the batched Cholesky), trtri, lauum = k_lauum2, other = k_finalize2,
  * build = k_build (kernel matrix), trace = k_grad_trace; flops_* = sum of N^3/3 over the slots evaluated */
 long long gpsat_launch_count(const gpsat_handle* h);
+/* Flag-wait timeouts of k_potrf_panel since the handle was created (0 on a healthy device; see GPSAT_ESYNC). */
+long long gpsat_sync_timeouts(gpsat_handle* h);
 int gpsat_set_profiling(gpsat_handle* h, int enabled);
 int gpsat_get_profile(gpsat_handle* h, double* ms_potrf, double* ms_trtri, double* ms_lauum,
                       double* ms_other, double* flops_potrf, double* flops_trtri, double* flops_lauum,
