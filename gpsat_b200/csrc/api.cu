@@ -62,6 +62,7 @@ struct gpsat_handle {
   int n_groups = 3;          // slot groups / streams of the optimiser (GPSAT_GROUPS overrides)
   cudaStream_t gstream[8] = {};
   cudaEvent_t gevent[8] = {};
+  cudaEvent_t gevent2[8][2] = {};   // census events of the optimiser rounds, [group][parity]
   cudaEvent_t ev_fork = nullptr;
   int groups_ready = 0;
   bool attrs_set = false;
@@ -149,7 +150,10 @@ extern "C" int gpsat_destroy(gpsat_handle* h) {
     if (b->p) cudaFree(b->p);
   if (h->host_ints) cudaFreeHost(h->host_ints);
   if (h->timeouts_dev) cudaFree(h->timeouts_dev);
-  for (int g = 0; g < h->groups_ready; ++g) { cudaStreamDestroy(h->gstream[g]); cudaEventDestroy(h->gevent[g]); }
+  for (int g = 0; g < h->groups_ready; ++g) {
+    cudaStreamDestroy(h->gstream[g]); cudaEventDestroy(h->gevent[g]);
+    cudaEventDestroy(h->gevent2[g][0]); cudaEventDestroy(h->gevent2[g][1]);
+  }
   if (h->ev_fork) cudaEventDestroy(h->ev_fork);
   for (auto e : h->ev) cudaEventDestroy(e);
   delete h;
@@ -250,9 +254,11 @@ static int ensure_groups(gpsat_handle* h, int G, int S) {
   for (int g = h->groups_ready; g < G; ++g) {
     CK(cudaStreamCreateWithFlags(&h->gstream[g], cudaStreamNonBlocking));
     CK(cudaEventCreateWithFlags(&h->gevent[g], cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&h->gevent2[g][0], cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&h->gevent2[g][1], cudaEventDisableTiming));
     h->groups_ready = g + 1;
   }
-  const size_t need = (size_t)MAX_GROUPS * 3 * S + 8;
+  const size_t need = (size_t)MAX_GROUPS * 2 * 3 * S + 8;
   if (h->host_ints_cap < need) {
     if (h->host_ints) cudaFreeHost(h->host_ints);
     h->host_ints = nullptr;
@@ -501,8 +507,17 @@ extern "C" int gpsat_gpr_optimise(gpsat_handle* h, const gpsat_batch* b, const d
   G = std::max(1, std::min(G, MAX_GROUPS));
   r = ensure_groups(h, G, S);
   if (r) return r;
-  struct Group { SlotCtx c; SlotAux a; int s0, Sg; bool done, pending; };
+  // The host only needs two numbers per group and round -- are there active slots, and the largest matrix among
+  // them (grid sizes) -- and both may be STALE: slots are refilled from a queue sorted by descending size, so the
+  // largest active matrix never grows, and a round launched for a group that has meanwhile finished is a handful of
+  // early-exit grids.  So the census that sizes round r is the one taken after round r - 1 - LOOKAHEAD: the host
+  // queues round r while round r - 1 is still running and the device never waits for the host between rounds
+  // (GPSAT_LOOKAHEAD=0 restores the lock-step loop; phase profiling uses it so that the per-round flop counts are exact).
+  struct Group { SlotCtx c; SlotAux a; int s0, Sg; bool done; long long rounds; int nact, nbm; double fl; };
   Group grp[MAX_GROUPS];
+  int lookahead = h->profiling ? 0 : 1;
+  if (const char* el = getenv("GPSAT_LOOKAHEAD")) lookahead = atoi(el) > 0 ? 1 : 0;
+  if (h->profiling) lookahead = 0;
   CK(cudaEventRecord(h->ev_fork, st));
   for (int g = 0; g < G; ++g) {
     Group& q = grp[g];
@@ -513,59 +528,80 @@ extern "C" int gpsat_gpr_optimise(gpsat_handle* h, const gpsat_batch* b, const d
     q.a.slot_expert += q.s0;
     q.a.states += q.s0;
     q.done = false;
-    q.pending = false;
+    q.rounds = 0;
+    q.nact = q.nbm = 0;
+    q.fl = 0;
     cudaStream_t sg = (G == 1) ? st : h->gstream[g];
     if (G > 1) CK(cudaStreamWaitEvent(sg, h->ev_fork, 0));
   }
   const long long max_rounds = (long long)(b->n_experts / std::max(1, S / G) + 2) * (od.maxfun + od.maxls + 2);
   int live = G;
-  // GPSAT_TRACE=<file>: per group and round, host time at which the previous round of the group was seen
-  // complete + the active-slot census (diagnostic: slot-pool utilisation over a batch)
+  // GPSAT_TRACE=<file>: per group and round, host time at which the round was queued + the census it was sized by
+  // (diagnostic: slot-pool utilisation over a batch, host gaps)
   FILE* trace = nullptr;
   if (const char* tp = getenv("GPSAT_TRACE")) trace = fopen(tp, "a");
   const auto t_trace0 = std::chrono::steady_clock::now();
-  if (trace) fprintf(trace, "# optimise E=%d S=%d G=%d\n", b->n_experts, S, G);
+  if (trace) fprintf(trace, "# optimise E=%d S=%d G=%d lookahead=%d\n", b->n_experts, S, G, lookahead);
+  // census buffers: [group][parity][3 * Sg] ints (n | nb | active), events [group][parity]
+  auto census_buf = [&](int g, long long c) { return h->host_ints + ((size_t)g * 2 + (size_t)(c & 1)) * 3 * S; };
+  auto queue_census = [&](int g, long long c, cudaStream_t sg) -> int {
+    Group& q = grp[g];
+    int* hi = census_buf(g, c);
+    for (int k = 0; k < 3; ++k)
+      CK(cudaMemcpyAsync(hi + k * q.Sg, w.c.n + (size_t)k * S + q.s0, (size_t)q.Sg * sizeof(int),
+                         cudaMemcpyDeviceToHost, sg));
+    CK(cudaEventRecord(h->gevent2[g][c & 1], sg));
+    return 0;
+  };
+  auto read_census = [&](int g, long long c) -> int {
+    Group& q = grp[g];
+    CK(cudaEventSynchronize(h->gevent2[g][c & 1]));
+    const int* hi = census_buf(g, c);
+    q.nact = 0; q.nbm = 0; q.fl = 0;
+    for (int k = 0; k < q.Sg; ++k) {
+      if (hi[2 * q.Sg + k]) {
+        ++q.nact;
+        q.nbm = std::max(q.nbm, hi[q.Sg + k]);
+        const double n = (double)hi[k];
+        q.fl += n * n * n / 3.0;
+      }
+    }
+    return 0;
+  };
   for (long long round = 0; round < max_rounds && live > 0; ++round) {
     for (int g = 0; g < G; ++g) {
       Group& q = grp[g];
       if (q.done) continue;
       cudaStream_t sg = (G == 1) ? st : h->gstream[g];
-      int* hi = h->host_ints + (size_t)g * 3 * S;
-      if (!q.pending) {     // first look at this group's slot table
-        for (int k = 0; k < 3; ++k)
-          CK(cudaMemcpyAsync(hi + k * q.Sg, w.c.n + (size_t)k * S + q.s0, (size_t)q.Sg * sizeof(int),
-                             cudaMemcpyDeviceToHost, sg));
-        CK(cudaEventRecord(h->gevent[g], sg));
-      }
-      CK(cudaEventSynchronize(h->gevent[g]));
-      int nact = 0, nbm = 0;
-      double fl = 0;
-      for (int k = 0; k < q.Sg; ++k) {
-        if (hi[2 * q.Sg + k]) {
-          ++nact;
-          nbm = std::max(nbm, hi[q.Sg + k]);
-          const double n = (double)hi[k];
-          fl += n * n * n / 3.0;
+      // census index -1 = the slot table after k_slot_init; census c >= 0 = the table after round c
+      if (q.rounds == 0) {
+        r = queue_census(g, -1 + 2, sg);      // parity slot of "-1" (kept distinct from census 0)
+        if (r) return r;
+        r = read_census(g, -1 + 2);
+        if (r) return r;
+      } else {
+        const long long c = q.rounds - 1 - lookahead;
+        if (c >= 0) {
+          r = read_census(g, c);
+          if (r) return r;
         }
       }
       if (trace)
-        fprintf(trace, "%lld,%d,%.1f,%d,%d,%.4g\n", round, g,
-                std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - t_trace0).count(), nact,
-                nbm, fl);
-      if (nact == 0) {
+        fprintf(trace, "%lld,%d,%.1f,%d,%d,%.4g\n", q.rounds, g,
+                std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - t_trace0).count(),
+                q.nact, q.nbm, q.fl);
+      if (q.nact == 0) {
         q.done = true;
         --live;
         continue;
       }
-      r = run_round(h, q.c, nbm, true, true, sg, fl);
+      r = run_round(h, q.c, q.nbm, true, true, sg, q.fl);
       if (r) return r;
       k_opt_step<<<q.Sg, NTHREADS, 0, sg>>>(q.c, q.a, bi, tr, lo, out);
       ++h->launches;
-      for (int k = 0; k < 3; ++k)
-        CK(cudaMemcpyAsync(hi + k * q.Sg, w.c.n + (size_t)k * S + q.s0, (size_t)q.Sg * sizeof(int),
-                           cudaMemcpyDeviceToHost, sg));
-      CK(cudaEventRecord(h->gevent[g], sg));
-      q.pending = true;
+      r = queue_census(g, q.rounds, sg);
+      if (r) return r;
+      ++q.rounds;
       if (h->profiling && h->ev_used > 4000) { CK(cudaStreamSynchronize(sg)); harvest_profile(h, true, true); }
     }
   }
@@ -1011,23 +1047,16 @@ extern "C" int gpsat_microbench(int device, int which, int param, int nk, double
     else r = time_launch([&] { k_dmma_chain<32><<<nsm, 128>>>(iters, buf); }, &ms);
     *tflops_out = 2.0 * 256 * (which == 5 ? 8 : 32) * (double)iters * 4 * nsm / (ms * 1e-3) / 1e12;
   } else if (which == 50 || which == 51) {
-    // task streams of nk k-tiles each (param = tasks per CTA): 50 = 128x64 core, two CTAs per SM; 51 = 128x128 core
+    // task streams of nk k-tiles each (param = tasks per CTA) with the 128x128 core (51)
     const long tiles_per_cta = 48;
-    const int ctas = (which == 50) ? 2 * nsm : nsm;
+    const int ctas = nsm;
     const size_t bytes = (size_t)ctas * tiles_per_cta * TILE_BYTES;
     CK(cudaMalloc(&buf, bytes + (size_t)ctas * 4 * TILE_BYTES));
     CK(cudaMemset(buf, 0, bytes));
     const int tasks = std::max(1, param);
     if (which == 50) {
-      auto kern = k_gemm3_bench<false, false>;
-      CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, G3_SMEM_ELEMS * 8));
-      CK(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-      int occ = 0;
-      CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, G3_THREADS, G3_SMEM_ELEMS * 8));
-      if (occ < 2) { cudaFree(buf); return fail(GPSAT_EINVAL, "128x64 core: occupancy " + std::to_string(occ) + " < 2"); }
-      r = time_launch([&] { kern<<<ctas, G3_THREADS, G3_SMEM_ELEMS * 8>>>(buf, tiles_per_cta, nk, tasks, buf + bytes / 8); }, &ms);
-      *tflops_out = 2.0 * 128 * 64 * 64 * (double)nk * tasks * ctas / (ms * 1e-3) / 1e12;
-    } else {
+      cudaFree(buf);
+      return fail(GPSAT_EINVAL, "the 128x64 two-CTA core was an experiment of round 1 and is no longer built");    } else {
       auto kern = k_gemm2_tasks_bench<false, false>;
       CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, G2_SMEM_ELEMS * 8));
       r = time_launch([&] { kern<<<ctas, NTHREADS, G2_SMEM_ELEMS * 8>>>(buf, tiles_per_cta, nk, tasks, buf + bytes / 8); }, &ms);

@@ -37,7 +37,10 @@ struct Acc2 {
 };
 
 struct Frag2 {
+  static constexpr bool kHalves = false;   // every warp owns all 64 rows of its slab
   int lane, warp, q, r, ta, tb, nb0;
+  __device__ __forceinline__ int mi_begin() const { return 0; }
+  __device__ __forceinline__ int mi_end() const { return 8; }
   __device__ __forceinline__ Frag2() {
     lane = threadIdx.x & 31;
     warp = threadIdx.x >> 5;
@@ -53,6 +56,41 @@ struct Frag2 {
   }
   __device__ __forceinline__ int row(int mi) const { return 8 * mi + q; }             // within tile ta
   __device__ __forceinline__ int col(int ni) const { return nb0 + 8 * ni + 2 * r; }   // within tile tb (and col+1)
+};
+
+// Warp map for DIAGONAL supertiles (output = tiles (0,0), (1,0), (1,1); tile (0,1) is the mirror image of (1,0) and
+// is not computed).  With the Frag2 map the two warps that own (0,1) would idle and the step would still take as
+// long as a full supertile (schedulers 0 and 1 keep two busy warps each).  Here the three tiles' six 64x32 slabs
+// are dealt so that EVERY scheduler gets three 32x32 blocks (a full slab + half a slab): a diagonal-supertile k-step
+// takes 3/4 of the time of a full one.
+//   scheduler 0: warp 0 = (0,0) cols  0-31 all rows   | warp 4 = (1,1) cols 32-63 rows  0-31
+//   scheduler 1: warp 1 = (0,0) cols 32-63 all rows   | warp 5 = (1,1) cols 32-63 rows 32-63
+//   scheduler 2: warp 2 = (1,0) cols  0-31 all rows   | warp 6 = (1,1) cols  0-31 rows  0-31
+//   scheduler 3: warp 3 = (1,0) cols 32-63 all rows   | warp 7 = (1,1) cols  0-31 rows 32-63
+struct Frag2D {
+  static constexpr bool kHalves = true;
+  int lane, warp, q, r, ta, tb, nb0, half;   // half: 0 = rows 0-63, 1 = rows 0-31 (mi 0..3), 2 = rows 32-63 (mi 4..7)
+  __device__ __forceinline__ Frag2D() {
+    lane = threadIdx.x & 31;
+    warp = threadIdx.x >> 5;
+    q = lane >> 2;
+    r = lane & 3;
+    if (warp < 4) {
+      ta = warp >> 1;            // warps 0,1 -> tile row 0; warps 2,3 -> tile row 1
+      tb = 0;
+      nb0 = (warp & 1) * 32;
+      half = 0;
+    } else {
+      ta = 1;
+      tb = 1;
+      nb0 = (warp < 6) ? 32 : 0;
+      half = 1 + (warp & 1);
+    }
+  }
+  __device__ __forceinline__ int mi_begin() const { return half == 2 ? 4 : 0; }
+  __device__ __forceinline__ int mi_end() const { return half == 1 ? 4 : 8; }
+  __device__ __forceinline__ int row(int mi) const { return 8 * mi + q; }
+  __device__ __forceinline__ int col(int ni) const { return nb0 + 8 * ni + 2 * r; }
 };
 
 // one thread: bulk-copy one 32-deep k-slice (16 KiB) of a tile into a shared-memory half
@@ -72,13 +110,14 @@ struct NoHook {
 };
 // `last_loads_done()` is invoked once, after the fragments of the LAST k-step have arrived in registers (this warp will
 // not read the slice again) and before that step's 32 DMMAs are issued: the ring uses it to release the slot early.
-template <bool TA, bool TBm, class FRAG, class HOOK>
-__device__ __forceinline__ void mma_half_h(Acc2& acc, const double* __restrict__ As, const double* __restrict__ Bs,
+// MI0 / MI1: the 8-row groups [MI0, MI1) of the slab this warp computes (0, 8 = the whole 64x32 slab).
+template <bool TA, bool TBm, int MI0, int MI1, class FRAG, class HOOK>
+__device__ __forceinline__ void mma_half_r(Acc2& acc, const double* __restrict__ As, const double* __restrict__ Bs,
                                            const FRAG& f, HOOK last_loads_done) {
   int aoff[8], boff[4];
   const int sq = (f.q & 3) << 2;
 #pragma unroll
-  for (int mi = 0; mi < 8; ++mi) {
+  for (int mi = MI0; mi < MI1; ++mi) {
     const int m = 8 * mi + f.q;
     aoff[mi] = TA ? ((m >> 5) * 1024 + f.r * 32 + ((m & 31) ^ (f.r << 2))) : (m * 32 + f.r);
   }
@@ -89,7 +128,7 @@ __device__ __forceinline__ void mma_half_h(Acc2& acc, const double* __restrict__
   }
   double a[2][8], b[2][4];
 #pragma unroll
-  for (int mi = 0; mi < 8; ++mi) a[0][mi] = As[aoff[mi] + (TA ? 0 : (0 ^ sq))];
+  for (int mi = MI0; mi < MI1; ++mi) a[0][mi] = As[aoff[mi] + (TA ? 0 : (0 ^ sq))];
 #pragma unroll
   for (int ni = 0; ni < 4; ++ni) b[0][ni] = Bs[boff[ni] + (TBm ? 0 : (0 ^ sq))];
 #pragma unroll
@@ -98,29 +137,40 @@ __device__ __forceinline__ void mma_half_h(Acc2& acc, const double* __restrict__
     if (ks + 1 < 8) {
       const int kk = (ks + 1) * 4;
 #pragma unroll
-      for (int mi = 0; mi < 8; ++mi) a[nxt][mi] = As[aoff[mi] + (TA ? kk * 32 : (kk ^ sq))];
+      for (int mi = MI0; mi < MI1; ++mi) a[nxt][mi] = As[aoff[mi] + (TA ? kk * 32 : (kk ^ sq))];
 #pragma unroll
       for (int ni = 0; ni < 4; ++ni) b[nxt][ni] = Bs[boff[ni] + (TBm ? kk * 32 : (kk ^ sq))];
     }
     if (ks == 7) {
-      // last step: eight DMMAs that between them read every fragment register first -- once they have issued, the
+      // last step: DMMAs that between them read every fragment register first -- once they have issued, the
       // scoreboard guarantees that all of this warp's shared-memory loads of the slice have returned -- then the
-      // hook, then the remaining 24 DMMAs (which hide whatever latency the hook started)
+      // hook, then the remaining DMMAs (which hide whatever latency the hook started)
 #pragma unroll
-      for (int mi = 0; mi < 8; ++mi)
+      for (int mi = MI0; mi < MI1; ++mi)
         dmma884(acc.c[mi][mi & 3][0], acc.c[mi][mi & 3][1], a[cur][mi], b[cur][mi & 3]);
       last_loads_done();
 #pragma unroll
-      for (int mi = 0; mi < 8; ++mi)
+      for (int mi = MI0; mi < MI1; ++mi)
 #pragma unroll
         for (int ni = 0; ni < 4; ++ni)
           if (ni != (mi & 3)) dmma884(acc.c[mi][ni][0], acc.c[mi][ni][1], a[cur][mi], b[cur][ni]);
     } else {
 #pragma unroll
-      for (int mi = 0; mi < 8; ++mi)
+      for (int mi = MI0; mi < MI1; ++mi)
 #pragma unroll
         for (int ni = 0; ni < 4; ++ni) dmma884(acc.c[mi][ni][0], acc.c[mi][ni][1], a[cur][mi], b[cur][ni]);
     }
+  }
+}
+template <bool TA, bool TBm, class FRAG, class HOOK>
+__device__ __forceinline__ void mma_half_h(Acc2& acc, const double* __restrict__ As, const double* __restrict__ Bs,
+                                           const FRAG& f, HOOK last_loads_done) {
+  if constexpr (FRAG::kHalves) {      // warp-uniform
+    if (f.half == 0) mma_half_r<TA, TBm, 0, 8>(acc, As, Bs, f, last_loads_done);
+    else if (f.half == 1) mma_half_r<TA, TBm, 0, 4>(acc, As, Bs, f, last_loads_done);
+    else mma_half_r<TA, TBm, 4, 8>(acc, As, Bs, f, last_loads_done);
+  } else {
+    mma_half_r<TA, TBm, 0, 8>(acc, As, Bs, f, last_loads_done);
   }
 }
 template <bool TA, bool TBm, class FRAG>
@@ -174,9 +224,9 @@ struct NoTail {
 // tail[e] (tile t at tail[e] + t * TILE_ELEMS, missing tiles are not touched).  Without TAIL the call ends with
 // every copy consumed and a __syncthreads(); with TAIL the caller reads the tiles and then must __syncthreads()
 // before the ring is reused.
-template <bool TA, bool TBm, bool TAIL, class FA, class FB, class FT>
+template <bool TA, bool TBm, bool TAIL, class FA, class FB, class FRAG, class FT>
 __device__ __forceinline__ void gemm2_pipeline_t(Acc2& acc, double* smem, G2Pipe& p, int kbeg, int kend, FA a_of,
-                                                 FB b_of, const Frag2& f, FT tail_of, const double** tail) {
+                                                 FB b_of, const FRAG& f, FT tail_of, const double** tail) {
   const int nsl = (kend > kbeg) ? 2 * (kend - kbeg) : 0;   // 32-deep slices
   const int ntot = nsl + (TAIL ? 2 : 0);
   if (ntot == 0) return;
@@ -242,9 +292,9 @@ __device__ __forceinline__ void gemm2_pipeline_t(Acc2& acc, double* smem, G2Pipe
   p.count += ntot;
 }
 
-template <bool TA, bool TBm, class FA, class FB>
+template <bool TA, bool TBm, class FA, class FB, class FRAG>
 __device__ __forceinline__ void gemm2_pipeline(Acc2& acc, double* smem, G2Pipe& p, int kbeg, int kend, FA a_of,
-                                               FB b_of, const Frag2& f) {
+                                               FB b_of, const FRAG& f) {
   gemm2_pipeline_t<TA, TBm, false>(acc, smem, p, kbeg, kend, a_of, b_of, f, NoTail(), nullptr);
 }
 
@@ -252,8 +302,10 @@ __device__ __forceinline__ void gemm2_pipeline(Acc2& acc, double* smem, G2Pipe& 
 template <class FRAG>
 __device__ __forceinline__ void store_acc2(double* __restrict__ tile, const Acc2& acc, const FRAG& f,
                                            double scale = 1.0) {
+  const int m0 = f.mi_begin(), m1 = f.mi_end();
 #pragma unroll
   for (int mi = 0; mi < 8; ++mi) {
+    if (mi < m0 || mi >= m1) continue;      // rows this warp does not own (Frag2D half slabs)
     const int m = f.row(mi);
 #pragma unroll
     for (int ni = 0; ni < 4; ++ni) {

@@ -383,60 +383,58 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_potrf_panel(SlotCtx c, int J, i
   double* Kt = c.Kt + (long)s * c.tile_stride;
   double* Xt = c.Xt + (long)s * c.tile_stride;
   const bool two = (j1 < nb);
-  Frag2 f;
   G2Pipe pipe;
   if (threadIdx.x == 0) {
     mbar_init(xbar, 1);
     mbar_init(xbar + 1, 1);
   }
   pipe.init();   // fences the mbarrier inits and syncs
-  // L_I,panel = [C0 C1] X_JJ' with X_JJ = [[X00, 0], [X10, X11]]:  column j0 = C0 X00',  column j1 = C0 X10' + C1 X11'.
-  // Step 1 (k = j1, column-j1 warps only) needs X11 alone: it is fetched early into the extra tile behind the ring,
-  // and X00 / X10 for step 2 land in the third ring slot while step 1 runs.
-  double* sC = smem;                          // 4 tile images (ta, tb) at (2 * ta + tb) * TILE_ELEMS
-  double* sX1 = smem + 4 * TILE_ELEMS;        // X00, X10 (two tile columns) -- third ring slot
-  double* sXe = smem + G2_SMEM_ELEMS;         // X11 (or X00 when the panel has one tile column) -- outside the ring
-  const double* xe_src = two ? tile_ptr(Xt, j1, j1) : tile_ptr(Xt, j0, j0);
-  bool xe_issued = false;
-  // (thread 32 owns the X_JJ fetches, so that thread 0 goes straight to the first ring copies)
-  if (I != J && threadIdx.x == 32 && ld_acquire_gpu(c.pflag + s) == J + 1) {   // already published: the common case
-    fence_proxy_async_all();
-    mbar_expect_tx(xbar, TILE_BYTES);
-    bulk_g2s(sXe, xe_src, TILE_BYTES, xbar);
-    xe_issued = true;
-  }
-  Acc2 acc;
-  acc.zero();
-  const int ti = 2 * I + f.ta, tj = j0 + f.tb;
-  const bool valid = (ti < nb) && (tj < nb) && (tj <= ti);
-  const double* ktile[2];
-  gemm2_pipeline_t<false, false, true>(
-      acc, smem, pipe, 0, j0,
-      [&](int k, int t) -> const double* { return (2 * I + t < nb) ? tile_ptr(Lt, 2 * I + t, k) : nullptr; },
-      [&](int k, int t) -> const double* { return (j0 + t < nb) ? tile_ptr(Lt, j0 + t, k) : nullptr; }, f,
-      [&](int e, int t) -> const double* {
-        const int a = 2 * I + e, b = j0 + t;
-        return (a < nb && b < nb && b <= a) ? tile_ptr(Kt, a, b) : nullptr;
-      },
-      ktile);
-  if (valid) {
-    const double* kt = ktile[f.ta] + f.tb * TILE_ELEMS;
-#pragma unroll
-    for (int mi = 0; mi < 8; ++mi)
-#pragma unroll
-      for (int ni = 0; ni < 4; ++ni) {
-        const double2 kv = *reinterpret_cast<const double2*>(kt + swz(f.row(mi), f.col(ni)));
-        acc.c[mi][ni][0] = kv.x - acc.c[mi][ni][0];
-        acc.c[mi][ni][1] = kv.y - acc.c[mi][ni][1];
-      }
-  }
-  __syncthreads();   // every warp has read its K tile: the ring is free
+  auto a_of = [&](int k, int t) -> const double* { return (2 * I + t < nb) ? tile_ptr(Lt, 2 * I + t, k) : nullptr; };
+  auto b_of = [&](int k, int t) -> const double* { return (j0 + t < nb) ? tile_ptr(Lt, j0 + t, k) : nullptr; };
+  auto k_of = [&](int e, int t) -> const double* {
+    const int a = 2 * I + e, b = j0 + t;
+    return (a < nb && b < nb && b <= a) ? tile_ptr(Kt, a, b) : nullptr;
+  };
   if (I != J) {
-    // ---- off-diagonal supertile: L_I,panel = C X_JJ' ----
+    // ---- off-diagonal supertile: C = K - sum_k L_Ik L_Jk', then L_I,panel = C X_JJ' ----
+    Frag2 f;
+    // L_I,panel = [C0 C1] X_JJ' with X_JJ = [[X00, 0], [X10, X11]]:  column j0 = C0 X00',  column j1 = C0 X10' + C1 X11'.
+    // Step 1 (k = j1, column-j1 warps only) needs X11 alone: it is fetched early into the extra tile behind the ring,
+    // and X00 / X10 for step 2 land in the third ring slot while step 1 runs.
+    double* sC = smem;                          // 4 tile images (ta, tb) at (2 * ta + tb) * TILE_ELEMS
+    double* sX1 = smem + 4 * TILE_ELEMS;        // X00, X10 (two tile columns) -- third ring slot
+    double* sXe = smem + G2_SMEM_ELEMS;         // X11 (or X00 when the panel has one tile column) -- outside the ring
+    const double* xe_src = two ? tile_ptr(Xt, j1, j1) : tile_ptr(Xt, j0, j0);
+    bool xe_issued = false;
+    // (thread 32 owns the X_JJ fetches, so that thread 0 goes straight to the first ring copies)
+    if (threadIdx.x == 32 && ld_acquire_gpu(c.pflag + s) == J + 1) {   // already published: the common case
+      fence_proxy_async_all();
+      mbar_expect_tx(xbar, TILE_BYTES);
+      bulk_g2s(sXe, xe_src, TILE_BYTES, xbar);
+      xe_issued = true;
+    }
+    Acc2 acc;
+    acc.zero();
+    const int ti = 2 * I + f.ta, tj = j0 + f.tb;
+    const bool valid = (ti < nb) && (tj < nb) && (tj <= ti);
+    const double* ktile[2];
+    gemm2_pipeline_t<false, false, true>(acc, smem, pipe, 0, j0, a_of, b_of, f, k_of, ktile);
+    if (valid) {
+      const double* kt = ktile[f.ta] + f.tb * TILE_ELEMS;
+#pragma unroll
+      for (int mi = 0; mi < 8; ++mi)
+#pragma unroll
+        for (int ni = 0; ni < 4; ++ni) {
+          const double2 kv = *reinterpret_cast<const double2*>(kt + swz(f.row(mi), f.col(ni)));
+          acc.c[mi][ni][0] = kv.x - acc.c[mi][ni][0];
+          acc.c[mi][ni][1] = kv.y - acc.c[mi][ni][1];
+        }
+    }
+    __syncthreads();   // every warp has read its K tile: the ring is free
     if (threadIdx.x == 32) {
       // Blocks are dispatched in index order, so the slot's diagonal CTA (index < S) is resident or finished by
       // the time this one runs and the wait is short.  It is bounded anyway (~1 s): a lost flag marks the slot
-      // as failed (objective = +inf) instead of hanging the device.
+      // as failed (objective = +inf) and is reported to the caller as GPSAT_ESYNC instead of hanging the device.
       int spins = 0;
       while (ld_acquire_gpu(c.pflag + s) != J + 1) {
         __nanosleep(200);
@@ -478,9 +476,32 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_potrf_panel(SlotCtx c, int J, i
     if (ti < nb && tj < nb) store_acc2(tile_ptr(Lt, ti, tj), acc, f);
     return;
   }
-  // ---- diagonal 128x128 block ----
+  // ---- diagonal 128x128 block: update of the three lower tiles with the balanced diagonal warp map (gemm2.cuh:
+  //      a k-step costs 3/4 of a full supertile's), then the in-CTA factorisation ----
+  Frag2D f;
+  Acc2 acc;
+  acc.zero();
+  const int ti = 2 * I + f.ta, tj = j0 + f.tb;
+  const bool valid = (ti < nb) && (tj < nb);
+  const double* ktile[2];
+  gemm2_pipeline_t<false, false, true>(acc, smem, pipe, 0, j0, a_of, b_of, f, k_of, ktile);
+  if (valid) {
+    const double* kt = ktile[f.ta] + f.tb * TILE_ELEMS;
+    const int m0 = f.mi_begin(), m1 = f.mi_end();
+#pragma unroll
+    for (int mi = 0; mi < 8; ++mi) {
+      if (mi < m0 || mi >= m1) continue;
+#pragma unroll
+      for (int ni = 0; ni < 4; ++ni) {
+        const double2 kv = *reinterpret_cast<const double2*>(kt + swz(f.row(mi), f.col(ni)));
+        acc.c[mi][ni][0] = kv.x - acc.c[mi][ni][0];
+        acc.c[mi][ni][1] = kv.y - acc.c[mi][ni][1];
+      }
+    }
+  }
+  __syncthreads();   // every warp has read its K tile: the ring is free
   double* dg = smem + G2_SMEM_ELEMS + TILE_ELEMS;
-  if (f.ta == 0 && f.tb == 0) {
+  if (f.ta == 0) {                        // tile (0,0): warps 0 and 1 hold all 64 rows of their slabs
 #pragma unroll
     for (int mi = 0; mi < 8; ++mi)
 #pragma unroll
@@ -488,10 +509,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_potrf_panel(SlotCtx c, int J, i
         smem[f.row(mi) * LDA + f.col(ni)] = acc.c[mi][ni][0];
         smem[f.row(mi) * LDA + f.col(ni) + 1] = acc.c[mi][ni][1];
       }
-  } else if (two && f.ta == 1 && f.tb == 0) {
+  } else if (two && f.tb == 0) {
     store_acc2(smem + DIAG_P1, acc, f);
-  } else if (two && f.ta == 1 && f.tb == 1) {
-    store_acc2(smem + DIAG_P2, acc, f);
+  } else if (two) {
+    store_acc2(smem + DIAG_P2, acc, f);   // (1,1): each of the four warps stores its 32 rows
   }
   diag_block_128(smem, dg, two, j0, N, c.fail + s, tile_ptr(Lt, j0, j0), two ? tile_ptr(Lt, j1, j0) : nullptr,
                  two ? tile_ptr(Lt, j1, j1) : nullptr, tile_ptr(Xt, j0, j0), two ? tile_ptr(Xt, j1, j0) : nullptr,
@@ -597,20 +618,25 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_lauum2(SlotCtx c) {
   tri_decode(blockIdx.x, I, J);
   if (I >= nsr) return;
   double* Kt = c.Kt + (long)s * c.tile_stride;
-  Frag2 f;
   G2Pipe pipe;
   pipe.init();
   Acc2 acc;
   acc.zero();
-  gemm2_pipeline<true, true>(
-      acc, smem, pipe, 2 * I, nb,
-      [&](int k, int t) -> const double* {
-        return (2 * I + t < nb && k >= 2 * I + t) ? x_tile(c, s, k, 2 * I + t) : nullptr;
-      },
-      [&](int k, int t) -> const double* {
-        return (2 * J + t < nb && k >= 2 * J + t) ? x_tile(c, s, k, 2 * J + t) : nullptr;
-      },
-      f);
+  auto a_of = [&](int k, int t) -> const double* {
+    return (2 * I + t < nb && k >= 2 * I + t) ? x_tile(c, s, k, 2 * I + t) : nullptr;
+  };
+  auto b_of = [&](int k, int t) -> const double* {
+    return (2 * J + t < nb && k >= 2 * J + t) ? x_tile(c, s, k, 2 * J + t) : nullptr;
+  };
+  if (I == J) {      // diagonal supertile: three tiles, balanced warp map (3/4 of a full supertile's time per k-step)
+    Frag2D f;
+    gemm2_pipeline<true, true>(acc, smem, pipe, 2 * I, nb, a_of, b_of, f);
+    const int ti = 2 * I + f.ta, tj = 2 * J + f.tb;
+    if (ti < nb && tj < nb) store_acc2(tile_ptr(Kt, ti, tj), acc, f);
+    return;
+  }
+  Frag2 f;
+  gemm2_pipeline<true, true>(acc, smem, pipe, 2 * I, nb, a_of, b_of, f);
   const int ti = 2 * I + f.ta, tj = 2 * J + f.tb;
   if (ti < nb && tj < nb && tj <= ti) store_acc2(tile_ptr(Kt, ti, tj), acc, f);
 }

@@ -4,7 +4,6 @@
 #include "gemm_core.cuh"
 #include "gemm2.cuh"
 #include "gpr2.cuh"
-#include "gemm3.cuh"
 
 namespace gpsat {
 
@@ -145,28 +144,9 @@ __global__ void __launch_bounds__(256) k_elem_accuracy(int mode, int per_thread,
   atomicMax(out, (unsigned long long)__double_as_longlong(worst));
 }
 
-// 128x64 core, two CTAs per SM (gemm3.cuh): mode 1 = stream nk k-tiles per CTA from a private region; each CTA runs
-// `tasks` such GEMMs back to back (prologue and epilogue store included), like the real short-loop kernels
-template <bool TA, bool TBm>
-__global__ void __launch_bounds__(G3_THREADS, 2) k_gemm3_bench(const double* tiles, long tiles_per_cta, int nk, int tasks,
-                                                               double* out) {
-  extern __shared__ __align__(128) double smem[];
-  Frag3 f;
-  G3Pipe pipe;
-  pipe.init();
-  const double* base = tiles + (long)blockIdx.x * tiles_per_cta * TILE_ELEMS;
-  double* dst = out + (long)blockIdx.x * 2 * TILE_ELEMS;
-  for (int t = 0; t < tasks; ++t) {
-    Acc2 acc;
-    acc.zero();
-    gemm3_pipeline<TA, TBm>(
-        acc, smem, pipe, 0, nk,
-        [&](int k, int tt) { return base + ((long)(3 * k + tt + t) % tiles_per_cta) * TILE_ELEMS; },
-        [&](int k) { return base + ((long)(3 * k + 2 + t) % tiles_per_cta) * TILE_ELEMS; }, f);
-    store_acc2(dst + f.ta * TILE_ELEMS, acc, f);
-  }
-}
-// the same experiment with the 128x128 core (one CTA per SM)
+// task streams with the 128x128 core (one CTA per SM): `tasks` GEMMs of nk k-tiles back to back, prologue and epilogue
+// store included, like the real short-loop kernels.  (The 128x64 two-CTAs-per-SM variant measured against it in round 1
+// -- +1.5-3 %, profiles/r01_microbench_2cta.json -- was not adopted and its code is no longer part of the library.)
 template <bool TA, bool TBm>
 __global__ void __launch_bounds__(NTHREADS, 1) k_gemm2_tasks_bench(const double* tiles, long tiles_per_cta, int nk,
                                                                    int tasks, double* out) {

@@ -47,7 +47,7 @@ def _frames(w, experts):
     return eloc, data, pred
 
 
-def _check_optimised(res, per, what):
+def _check_optimised(res, per, what, rtol_var=RTOL_OPT_PRED):
     """res: run_experts_host output; per: the oracle's per-expert records (same expert order)."""
     ooff, poff = res["obs_offsets"], res["pred_offsets"]
     assert res["n_valid"] == len([p for p in per if not p["skipped"]])
@@ -66,10 +66,10 @@ def _check_optimised(res, per, what):
         worst["var"] = max(worst["var"], np.abs(res["fvar"][sl] - v_ref).max() / np.abs(v_ref).max())
         np.testing.assert_allclose(res["fmean"][sl], m_ref, rtol=RTOL_OPT_PRED,
                                    atol=RTOL_OPT_PRED * np.abs(m_ref).max(), err_msg=f"{what} expert {k} f*")
-        np.testing.assert_allclose(res["fvar"][sl], v_ref, rtol=RTOL_OPT_PRED,
-                                   atol=RTOL_OPT_PRED * np.abs(v_ref).max(), err_msg=f"{what} expert {k} f*_var")
-        np.testing.assert_allclose(res["yvar"][sl], pe["pred"]["y_var"], rtol=RTOL_OPT_PRED,
-                                   atol=RTOL_OPT_PRED * np.abs(v_ref).max(), err_msg=f"{what} expert {k} y_var")
+        np.testing.assert_allclose(res["fvar"][sl], v_ref, rtol=rtol_var,
+                                   atol=rtol_var * np.abs(v_ref).max(), err_msg=f"{what} expert {k} f*_var")
+        np.testing.assert_allclose(res["yvar"][sl], pe["pred"]["y_var"], rtol=rtol_var,
+                                   atol=rtol_var * np.abs(v_ref).max(), err_msg=f"{what} expert {k} y_var")
     print(f"{what}: worst (f_gpu - f_ref)/|f_ref| = {worst['lml']:.3e}, mean {worst['mean']:.3e}, "
           f"var {worst['var']:.3e} (relative to the vector's max)")
 
@@ -236,4 +236,12 @@ def test_c5_shape_sgpr_m500(eng):
     res = dict(res, fobj=-res["fobj"])
     for pe in per:
         pe["objective"] = -pe["objective"]
-    _check_optimised(res, per, "c5")
+    # Optimised runs: the bound reached must be within 1e-6 of the oracle's and the predictive mean within 1e-4, as
+    # for the exact model.  The predictive VARIANCE is compared at 1e-3: with M = 500 and gpflow's 1e-6 jitter the
+    # gradient of the collapsed bound is a difference of terms ~1e6 times larger than itself (K_uu^-1 against
+    # Sigma^-1), so any float64 implementation -- this one, the oracle, gpflow's autodiff -- carries ~1e-6 relative
+    # noise in the gradient (tests/test_gpu_sgpr.py compares it at 2e-6); L-BFGS trajectories then part ways and stop
+    # at different points of the flat ridge the optimum sits on here (both lengthscales at their upper bounds), which
+    # moves kernel_variance by ~8e-4 and with it f*_var (= kernel_variance / 140 at these points) by ~5e-4 -- at FIXED
+    # parameters the same predictions agree to 4e-13 (printed above).
+    _check_optimised(res, per, "c5", rtol_var=1e-3)
