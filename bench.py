@@ -59,6 +59,7 @@ def parse():
                     help="experts of the fixed CPU sample (the first K of the fixed-seed expert order): timed by the "
                          "cpu_baseline leg, and spread over the steps of --impl reference")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--skip-e2e", action="store_true", help="sweeps only: leave the host-buffer leg out (e2e: null)")
     ap.add_argument("--strong", action="store_true", help="one fixed list of --total-experts for every N")
     ap.add_argument("--total-experts", type=int, default=8192)
     return ap.parse_args()
@@ -323,6 +324,7 @@ def run_b200(args):
             nfev_max = max(nfev_max, int(nf.max()))
         nobs.append(scalar(r["num_obs"]))
     ev1.record()
+    slot_plan = eng.last_plan()
     barrier()
     # device events on this rank's stream, max over ranks; the sharded step ends with host work (merge), so the
     # wall clock is taken too and the larger of the two counts
@@ -363,20 +365,23 @@ def run_b200(args):
     eng.set_profiling(False)
 
     # ---- end to end through the host-buffer API ----
-    step_host(args.warmup + args.steps)
-    barrier()
-    t0 = time.perf_counter()
-    ev0.record()
-    n_e2e, d2h = 0, 0
-    for s in range(args.steps):
-        r = step_host(args.warmup + args.steps + 1 + s)
-        n_e2e += int(r["n_valid"])
-        d2h = sum(v.nbytes for v in r.values() if isinstance(v, np.ndarray))
-    ev1.record()
-    barrier()
-    ms_e2e = max(maxreduce(ev0.elapsed_time(ev1)), maxreduce((time.perf_counter() - t0) * 1e3))
-    e2e_value = float(n_e2e) / (ms_e2e * 1e-3)
-    h2d = h2d_bytes(table_h, pred_h) + L * w["experts"].shape[1] * 8
+    e2e = None
+    if not args.skip_e2e:
+        step_host(args.warmup + args.steps)
+        barrier()
+        t0 = time.perf_counter()
+        ev0.record()
+        n_e2e, d2h = 0, 0
+        for s in range(args.steps):
+            r = step_host(args.warmup + args.steps + 1 + s)
+            n_e2e += int(r["n_valid"])
+            d2h = sum(v.nbytes for v in r.values() if isinstance(v, np.ndarray))
+        ev1.record()
+        barrier()
+        ms_e2e = max(maxreduce(ev0.elapsed_time(ev1)), maxreduce((time.perf_counter() - t0) * 1e3))
+        h2d = h2d_bytes(table_h, pred_h) + L * w["experts"].shape[1] * 8
+        e2e = {"value": float(n_e2e) / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(h2d),
+               "d2h_bytes_per_step": int(d2h)}
 
     if rank != 0:
         if world > 1:
@@ -436,10 +441,9 @@ def run_b200(args):
                                    "experts) through one batched optimise+predict call per GPU" +
                                    ("" if world == 1 else "; the list is LPT-sharded over the ranks and gathered once"),
                        "mean_obs_per_expert": float(np.mean(nobs)), "mean_nfev": nfev_sum / max(n_done, 1),
-                       "max_nfev": nfev_max, "sharding": sharding,
+                       "max_nfev": nfev_max, "sharding": sharding, "slot_plan_rank0": slot_plan,
                        "l2": "inputs larger than L2 (factor workspaces are GBs per step)"},
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
-            "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu}
+            "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu}
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

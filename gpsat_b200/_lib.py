@@ -98,6 +98,8 @@ _EXPORTS = {
                                      C.c_void_p]),
     "gpsat_launch_count": (C.c_longlong, [C.c_void_p]),
     "gpsat_sync_timeouts": (C.c_longlong, [C.c_void_p]),
+    "gpsat_last_plan": (C.c_int, [C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_size_t),
+                                  C.POINTER(C.c_size_t)]),
     "gpsat_set_profiling": (C.c_int, [C.c_void_p, C.c_int]),
     "gpsat_get_profile": (C.c_int, [C.c_void_p] + [C.POINTER(C.c_double)] * 9),
     "gpsat_gaussian_smooth": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_longlong, C.c_void_p, C.c_void_p,

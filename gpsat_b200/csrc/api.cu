@@ -66,6 +66,8 @@ struct gpsat_handle {
   cudaEvent_t ev_fork = nullptr;
   int groups_ready = 0;
   bool attrs_set = false;
+  int plan_slots = 0, plan_nbmax = 0;   // last make_plan (gpsat_last_plan)
+  size_t plan_bytes_per_slot = 0;
   int* timeouts_dev = nullptr;   // [1] flag-wait timeouts of k_potrf_panel (device counter, see GPSAT_ESYNC)
   long long timeouts_seen = 0;   // value already reported to the caller
 };
@@ -161,6 +163,15 @@ extern "C" int gpsat_destroy(gpsat_handle* h) {
 }
 
 extern "C" long long gpsat_launch_count(const gpsat_handle* h) { return h ? h->launches : 0; }
+extern "C" int gpsat_last_plan(const gpsat_handle* h, int* slots, int* nbmax, size_t* bytes_per_slot,
+                               size_t* budget_bytes) {
+  if (!h) return GPSAT_EINVAL;
+  if (slots) *slots = h->plan_slots;
+  if (nbmax) *nbmax = h->plan_nbmax;
+  if (bytes_per_slot) *bytes_per_slot = h->plan_bytes_per_slot;
+  if (budget_bytes) *budget_bytes = h->budget;
+  return 0;
+}
 extern "C" long long gpsat_sync_timeouts(gpsat_handle* h) {
   if (!h || !h->timeouts_dev) return 0;
   int v = 0;
@@ -229,6 +240,7 @@ static int make_plan(gpsat_handle* h, const gpsat_batch* b, Plan& pl, size_t ext
   long long cap = (long long)(h->budget / per);
   if (cap < 1) return fail(GPSAT_ENOMEM, "one expert of this size does not fit the memory budget");
   pl.S = (int)std::min<long long>(std::min<long long>(E, cap), h->max_slots > 0 ? h->max_slots : 4LL * h->n_sm);
+  h->plan_slots = pl.S; h->plan_nbmax = pl.nbmax; h->plan_bytes_per_slot = per;
   return 0;
 }
 

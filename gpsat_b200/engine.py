@@ -421,6 +421,16 @@ class Engine:
     def launch_count(self):
         return int(self.lib.gpsat_launch_count(self.h))
 
+    def sync_timeouts(self):
+        return int(self.lib.gpsat_sync_timeouts(self.h))
+
+    def last_plan(self):
+        """slot plan of the last batched call: resident experts, tile rows of the largest matrix, memory"""
+        s, nb, per, bud = C.c_int(), C.c_int(), C.c_size_t(), C.c_size_t()
+        _lib.check(self.lib.gpsat_last_plan(self.h, C.byref(s), C.byref(nb), C.byref(per), C.byref(bud)))
+        return {"slots": s.value, "max_obs_padded": nb.value * 64, "bytes_per_slot": per.value,
+                "workspace_bytes": s.value * per.value, "budget_bytes": bud.value}
+
     def set_profiling(self, on=True):
         _lib.check(self.lib.gpsat_set_profiling(self.h, int(on)))
 

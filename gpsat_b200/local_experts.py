@@ -567,8 +567,13 @@ class LocalExpertOI:
             cntk = np.diff(poff)[vpos[k]]
             sel = np.concatenate([np.arange(poff[v], poff[v + 1]) for v in vpos[k]])
             dim0 = np.concatenate([np.arange(c) for c in cntk])
+            f_bar = np.repeat(res["obs_mean"][vpos[k]], cntk)
+            if self.model_config["init_params"].get("obs_mean", None) != "local":
+                # base_model.py:199-200: without obs_mean='local' the mean is the INTEGER array [[0]], and predict
+                # broadcasts it (gpflow_models.py:265-271): the stored column is int64 zeros, not float
+                f_bar = np.zeros(len(f_bar), dtype=np.int64)
             pr = {"_dim_0": dim0, "f*": res["fmean"][sel], "f*_var": res["fvar"][sel], "y_var": res["yvar"][sel],
-                  "f_bar": np.repeat(res["obs_mean"][vpos[k]], cntk)}
+                  "f_bar": f_bar}
             for ci, c in enumerate(coords_col):
                 pr[f"pred_loc_{c}"] = res["pred_coords"][sel, ci]
             pr["_pos_"] = np.repeat(pp[k], cntk)

@@ -215,6 +215,9 @@ int gpsat_debug_factor(gpsat_handle* h, const gpsat_batch* b, const double* thet
  * potrf = k_potrf_* + k_quad (the batched Cholesky), trtri, lauum = k_lauum2, other = k_finalize2,
  * build = k_build (kernel matrix), trace = k_grad_trace; flops_* = sum of N^3/3 over the slots evaluated */
 long long gpsat_launch_count(const gpsat_handle* h);
+/* Slot plan of the last batched call on this handle: resident experts (slots), 64-row blocks of the largest
+ * matrix, bytes of workspace per slot and the memory budget the plan was fitted to.  Any pointer may be NULL. */
+int gpsat_last_plan(const gpsat_handle* h, int* slots, int* nbmax, size_t* bytes_per_slot, size_t* budget_bytes);
 /* Flag-wait timeouts of k_potrf_panel since the handle was created (0 on a healthy device; see GPSAT_ESYNC). */
 long long gpsat_sync_timeouts(gpsat_handle* h);
 int gpsat_set_profiling(gpsat_handle* h, int enabled);

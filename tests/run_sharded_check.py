@@ -30,11 +30,27 @@ def main():
                model_config=w["model"],
                pred_loc_config={"method": "from_dataframe", "df": ploc, "max_dist": w["max_dist"]})
     tabs = LocalExpertOI(device=local, **cfg).run(store_path=None)
+    # sparse model: the inducing points are drawn with numpy's global RNG in expert order (gpflow_models.py:809-819);
+    # every rank draws for the WHOLE list so a shard sees the single-GPU draws, and the points come back in the gather
+    cfg_s = dict(cfg, model_config=dict(w["model"], oi_model="B200SGPRModel",
+                                        init_params=dict(w["model"]["init_params"], num_inducing_points=40)))
+    np.random.seed(7)
+    tabs_s = LocalExpertOI(device=local, **cfg_s).run(store_path=None)
     dist.barrier()
     rank = dist.get_rank()
     world = dist.get_world_size()
     dist.destroy_process_group()
     if rank == 0:
+        np.random.seed(7)
+        single_s = LocalExpertOI(device=local, **cfg_s).run(store_path=None)
+        assert len(tabs_s["inducing_points"]) == len(single_s["inducing_points"]) > 0
+        for k in ("run_details", "preds", "lengthscales", "kernel_variance", "likelihood_variance", "inducing_points"):
+            a, b = tabs_s[k], single_s[k]
+            assert a.index.equals(b.index), "sparse " + k
+            for c in a.columns:
+                if c != "run_time" and a[c].dtype.kind == "f":
+                    np.testing.assert_array_equal(a[c].values, b[c].values, err_msg=f"sparse {k}.{c}")
+        print(f"sparse sharded run == single-GPU run: OK ({len(tabs_s['inducing_points'])} inducing-point rows)")
         single = LocalExpertOI(device=local, **cfg).run(store_path=None)
         for k in ("run_details", "preds", "lengthscales", "kernel_variance", "likelihood_variance"):
             a, b = tabs[k], single[k]
