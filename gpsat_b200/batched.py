@@ -274,9 +274,37 @@ def run_experts_host(eng: Engine, spec: ModelSpec, table, table_cols, obs_col, c
     res = run_experts(eng, spec, up(table), table_cols, obs_col, coords_col, up(experts), ref_cols, local_select,
                       pred_table_dev=up(pred_table), pred_cols=pred_cols, max_dist=max_dist, optimise=optimise,
                       predict=predict, min_obs=min_obs, theta_init=theta_init, count_only=count_only)
-    out = {}
-    for k, v in res.items():
-        out[k] = v.cpu().numpy() if isinstance(v, torch.Tensor) else v
+    return to_host(res, dev)
+
+
+_PINNED = {}     # (device index) -> grow-only pinned staging buffer (uint8)
+
+
+def to_host(res: dict, dev) -> dict:
+    """All device tensors of a result dict to numpy through ONE pinned staging buffer and ONE synchronisation
+    (a ``.cpu()`` per tensor is a pageable, synchronous copy each: the predict-only workload returns ~100 MB)."""
+    items = [(k, v) for k, v in res.items() if isinstance(v, torch.Tensor) and v.is_cuda]
+    out = {k: (v.numpy() if isinstance(v, torch.Tensor) else v) for k, v in res.items()
+           if not (isinstance(v, torch.Tensor) and v.is_cuda)}
+    if not items:
+        return out
+    sizes = [((v.numel() * v.element_size() + 63) // 64) * 64 for _, v in items]
+    total = max(sum(sizes), 64)
+    key = dev.index if hasattr(dev, "index") else int(dev)
+    buf = _PINNED.get(key)
+    if buf is None or buf.numel() < total:
+        buf = _PINNED[key] = torch.empty(total + total // 4, dtype=torch.uint8, pin_memory=True)
+    off = 0
+    views = []
+    for (k, v), sz in zip(items, sizes):
+        nbytes = v.numel() * v.element_size()
+        dst = buf[off:off + nbytes].view(v.dtype).reshape(v.shape)
+        dst.copy_(v.contiguous(), non_blocking=True)
+        views.append((k, dst))
+        off += sz
+    torch.cuda.current_stream(dev).synchronize()
+    for k, dst in views:
+        out[k] = dst.numpy().copy()          # the staging buffer is reused by the next call
     return out
 
 

@@ -236,3 +236,42 @@ def test_sgpr_with_all_points_reproduces_exact_gpr(golden_dir):
     # (the reference's own test has its LML assertion commented out, tests/test_localexperts.py:247)
     assert 0.0 < float(g["ml"]) - m.get_objective_function_value() < 0.3
     assert m.param_names[-1] == "inducing_points"
+
+
+@pytest.mark.parametrize("kernel,nu", [("Matern52", 2.5), ("Matern12", 0.5), ("Matern32", 1.5), ("RBF", None)])
+def test_all_kernel_families_vs_sklearn_ard(kernel, nu):
+    """Every kernel family of row K1 (gpflow.kernels.Matern12 / Matern32 / Matern52 / SquaredExponential) pinned to an
+    independent implementation: sklearn's ARD ``ConstantKernel * Matern(nu)`` / ``RBF`` with fixed hyper-parameters
+    (the construction GPSat's own sklearnGPRModel and tests/test_localexperts.py:25-49 use), in 3-D with
+    GPSat-like scales: kernel matrix, LML, predictive mean and variance."""
+    skl = pytest.importorskip("sklearn.gaussian_process")
+    from sklearn.gaussian_process.kernels import RBF, ConstantKernel, Matern
+    rng = np.random.default_rng(52)
+    n, P = 300, 40
+    X = np.column_stack([rng.uniform(-6, 6, (n, 2)), rng.integers(-4, 5, n).astype(float)])
+    y = 0.1 * np.sin(X[:, 0] / 2) + 0.05 * np.cos(X[:, 1] / 1.5) + rng.normal(0, 0.05, n)
+    Xs = np.column_stack([rng.uniform(-5, 5, (P, 2)), np.zeros(P)])
+    ls, kvar, nvar = np.array([5.18, 3.22, 9.0]), 0.015, 0.0033
+    base = RBF(length_scale=ls) if nu is None else Matern(length_scale=ls, nu=nu)
+    k = ConstantKernel(kvar) * base
+    np.testing.assert_allclose(gpr.kernel_matrix(X, Xs, ls, kvar, kernel), k(X, Xs), rtol=1e-12, atol=1e-18)
+    gp = skl.GaussianProcessRegressor(kernel=k, alpha=nvar, optimizer=None).fit(X, y)
+    lml_ref = gp.log_marginal_likelihood_value_
+    assert abs(gpr.lml(X, y, ls, kvar, nvar, kernel) - lml_ref) <= 1e-10 * abs(lml_ref)
+    m_ref, sd_ref = gp.predict(Xs, return_std=True)
+    m, v, yv = gpr.predict(X, y, Xs, ls, kvar, nvar, kernel)
+    np.testing.assert_allclose(m, m_ref, rtol=1e-9, atol=1e-12)
+    np.testing.assert_allclose(v, sd_ref ** 2, rtol=1e-8, atol=1e-14)
+    np.testing.assert_allclose(yv, v + nvar, rtol=1e-15)
+    # the gradient of the restated objective for this family against central differences of it
+    th = np.r_[ls, kvar, nvar]
+    f0, g = gpr.neg_lml_and_grad(X, y, ls, kvar, nvar, kernel)
+    assert abs(f0 + lml_ref) <= 1e-10 * abs(lml_ref)
+    for j in range(5):
+        h = 1e-6 * th[j]
+        tp, tm = th.copy(), th.copy()
+        tp[j] += h
+        tm[j] -= h
+        fd = (gpr.neg_lml_and_grad(X, y, tp[:3], tp[3], tp[4], kernel)[0] -
+              gpr.neg_lml_and_grad(X, y, tm[:3], tm[3], tm[4], kernel)[0]) / (2 * h)
+        assert abs(fd - g[j]) <= 2e-5 * max(1.0, abs(g[j])), (kernel, j, fd, g[j])
