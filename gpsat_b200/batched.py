@@ -277,12 +277,11 @@ def run_experts_host(eng: Engine, spec: ModelSpec, table, table_cols, obs_col, c
     return to_host(res, dev)
 
 
-_PINNED = {}     # (device index) -> grow-only pinned staging buffer (uint8)
-
-
 def to_host(res: dict, dev) -> dict:
-    """All device tensors of a result dict to numpy through ONE pinned staging buffer and ONE synchronisation
-    (a ``.cpu()`` per tensor is a pageable, synchronous copy each: the predict-only workload returns ~100 MB)."""
+    """All device tensors of a result dict to numpy through ONE pinned buffer and ONE synchronisation (a ``.cpu()`` per
+    tensor is a pageable, synchronous copy each: the predict-only workload returns ~100 MB).  The returned arrays are
+    views of that buffer, which they keep alive; torch's caching host allocator recycles it once they are dropped, so
+    steady-state calls neither page-lock new memory nor copy a second time."""
     items = [(k, v) for k, v in res.items() if isinstance(v, torch.Tensor) and v.is_cuda]
     out = {k: (v.numpy() if isinstance(v, torch.Tensor) else v) for k, v in res.items()
            if not (isinstance(v, torch.Tensor) and v.is_cuda)}
@@ -290,10 +289,7 @@ def to_host(res: dict, dev) -> dict:
         return out
     sizes = [((v.numel() * v.element_size() + 63) // 64) * 64 for _, v in items]
     total = max(sum(sizes), 64)
-    key = dev.index if hasattr(dev, "index") else int(dev)
-    buf = _PINNED.get(key)
-    if buf is None or buf.numel() < total:
-        buf = _PINNED[key] = torch.empty(total + total // 4, dtype=torch.uint8, pin_memory=True)
+    buf = torch.empty(total, dtype=torch.uint8, pin_memory=True)
     off = 0
     views = []
     for (k, v), sz in zip(items, sizes):
@@ -304,7 +300,7 @@ def to_host(res: dict, dev) -> dict:
         off += sz
     torch.cuda.current_stream(dev).synchronize()
     for k, dst in views:
-        out[k] = dst.numpy().copy()          # the staging buffer is reused by the next call
+        out[k] = dst.numpy()
     return out
 
 
