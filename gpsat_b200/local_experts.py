@@ -232,17 +232,30 @@ class LocalExpertOI:
         else:
             self.model = oi_model
         assert self.model in (B200GPRModel, B200SGPRModel), "the batched driver dispatches B200GPRModel / B200SGPRModel"
-        assert replacement_threshold is None, "replacement models are not supported by the batched dispatch"
-        self.model_config = dict(init_params=init_params or {}, constraints=constraints,
-                                 optim_kwargs=optim_kwargs or {},
-                                 oi_model="B200SGPRModel" if self.model is B200SGPRModel else "B200GPRModel")
+
+        def mc(model, ip, cons, ok):
+            return dict(init_params=ip or {}, constraints=cons, optim_kwargs=ok or {},
+                        oi_model="B200SGPRModel" if model is B200SGPRModel else "B200GPRModel")
+
+        self.model_config = mc(self.model, init_params, constraints, optim_kwargs)
         self.pred_kwargs = pred_kwargs or {}
         assert not self.pred_kwargs.get("full_cov", False), "full_cov predictions are not stored by run()"
         self.load_params_config = load_params
-        if load_params is not None:
-            assert not load_params.get("previous", False), \
-                "load_params={'previous': True} makes experts order-dependent and cannot be batched"
         self.params_to_store = None if params_to_store == "all" else params_to_store
+        # Two features make experts order-dependent or pick the model per expert -- load_params={"previous": True}
+        # (EMA warm start, local_experts.py:1079-1083,1200-1217) and replacement_threshold (:1021-1041).  They are
+        # served by the sequential fallback of run(): the same engine, one expert per call, in list order.
+        self.replacement_threshold = replacement_threshold
+        self.replacement_model_config = None
+        if replacement_threshold is not None:
+            rm = self.model if replacement_model is None else _get_model(replacement_model)
+            assert rm in (B200GPRModel, B200SGPRModel), "replacement_model must be a gpsat_b200 model"
+            self.replacement_model = rm
+            self.replacement_model_config = mc(rm, init_params if replacement_init_params is None else
+                                               replacement_init_params,
+                                               constraints if replacement_constraints is None else
+                                               replacement_constraints, replacement_optim_kwargs)
+            assert not (replacement_pred_kwargs or {}).get("full_cov", False)
 
     def set_pred_loc(self, method="expert_loc", coords_col=None, df=None, df_file=None, max_dist=None,
                      copy_df=False, **kwargs):
@@ -402,6 +415,13 @@ class LocalExpertOI:
                            and self._same_param_table(store_path, table_suffix))
         rows = xprt.to_dict("records")
         cache_key, cache_df = None, None
+        previous = bool((self.load_params_config or {}).get("previous", False))
+        if previous or self.replacement_threshold is not None:
+            assert not multi, "the sequential fallback (previous / replacement_threshold) runs on one GPU"
+            self._run_sequential(eng, xprt, rows, table_cols, ref_cols, pred_tab, pred_cols, store_path, store_every,
+                                 optimise, predict, min_obs, table_suffix, model_name, dev_name, config_id, D,
+                                 save_params, previous, out_tables if return_tables else None)
+            xprt = xprt.iloc[:0]      # nothing left for the batched loop
         for c0 in range(0, len(xprt), max_batch):
             members_all = np.arange(c0, min(c0 + max_batch, len(xprt)))
             # group the chunk's experts by their global where list (local_experts.py:426-472)
@@ -463,6 +483,91 @@ class LocalExpertOI:
         if not return_tables:
             return None
         return {k: (pd.concat(v, axis=0) if isinstance(v, list) else v) for k, v in out_tables.items()}
+
+    def _global_frame(self, where, cache):
+        """the observations passing the global where list, cached while consecutive experts share it"""
+        k = json.dumps(where, default=str, sort_keys=True)
+        if cache.get("key") != k:
+            base = ([self.data_where] if isinstance(self.data_where, dict) else list(self.data_where or []))
+            cache["df"] = dl.load(source=self.data_source, table=self.data_table, where=base + where,
+                                  col_funcs=self.col_funcs, row_select=self.row_select, col_select=self.col_select,
+                                  reset_index=True)
+            cache["key"] = k
+        return cache["df"]
+
+    def _run_sequential(self, eng, xprt, rows, table_cols, ref_cols, pred_tab, pred_cols, store_path, store_every,
+                        optimise, predict, min_obs, table_suffix, model_name, dev_name, config_id, D, save_params,
+                        previous, out_tables):
+        """The reference's loop order for the two order-dependent features (local_experts.py:930-1260): one expert per
+        engine call; ``previous`` starts every expert from the exponential moving average (rho = 0.95) of the
+        parameters of the experts that optimised successfully before it (:1200-1217); ``replacement_threshold``
+        switches to the replacement model's settings when an expert has fewer observations (:1021-1041)."""
+        spec_main = ModelSpec.from_model_config(self.model_config)
+        spec_repl = None if self.replacement_model_config is None else \
+            ModelSpec.from_model_config(self.replacement_model_config)
+        prev = None                     # EMA of theta [D+2]
+        pending, n_pending = {}, 0
+        cache = {}
+        is_writer = True
+
+        def flush():
+            nonlocal pending, n_pending
+            chunk = {}
+            for name, lst in sorted(pending.items(), key=lambda kv: {"run_details": 0, "preds": 1}.get(kv[0], 2)):
+                chunk[f"{name}{table_suffix}"] = pd.concat(lst, axis=0).drop(columns="_pos_")
+            if store_path is not None and is_writer:
+                self._flush(store_path, chunk)
+            if out_tables is not None:
+                for name, df in chunk.items():
+                    out_tables.setdefault(name, []).append(df)
+            pending, n_pending = {}, 0
+
+        for i in range(len(xprt)):
+            sub = xprt.iloc[[i]]
+            where = dl.get_where_list(self.global_select, self.local_select, rows[i])
+            gdf = self._global_frame(where, cache)
+            table = np.ascontiguousarray(gdf[table_cols].values.T, dtype=np.float64) if len(gdf) else \
+                np.zeros((len(table_cols), 1)) + np.inf
+            refs = np.ascontiguousarray(sub[ref_cols].values, dtype=np.float64)
+            kw = dict(pred_table=pred_tab, pred_cols=pred_cols, max_dist=self.pred_max_dist, min_obs=min_obs)
+            spec, mname = spec_main, model_name
+            if spec_repl is not None:
+                cnt = run_experts_sharded(eng, spec_main, table, table_cols, self.obs_col, self.coords_col, refs,
+                                          ref_cols, self.local_select, count_only=True, **kw)
+                if int(cnt["num_obs"][0]) < self.replacement_threshold:
+                    spec, mname = spec_repl, pretty_print_class(self.replacement_model)[:64]
+            theta_init, ok = None, np.ones(1, dtype=bool)
+            if previous:
+                if prev is None:        # the first model's parameters as constructed (local_experts.py:1051-1052)
+                    prev = HyperParams(D, spec.lengthscales, spec.kernel_variance, spec.likelihood_variance).theta()
+                theta_init = prev[None, :].copy()
+            elif self.load_params_config is not None:
+                theta_init, ok = self._load_theta(sub)
+            t0 = time.perf_counter()
+            pieces = {}
+            if ok[0]:
+                res = run_experts_sharded(eng, spec, table, table_cols, self.obs_col, self.coords_col, refs, ref_cols,
+                                          self.local_select, optimise=optimise, predict=predict,
+                                          theta_init=theta_init, **kw)
+                res_bad = None
+            else:
+                res = None
+                res_bad = run_experts_sharded(eng, spec, table, table_cols, self.obs_col, self.coords_col, refs,
+                                              ref_cols, self.local_select, count_only=True, **kw)
+            self._shape_tables(pieces, res, res_bad, sub, np.array([i]), ok, time.perf_counter() - t0, optimise,
+                               predict, mname, dev_name, config_id, D, save_params)
+            if res is not None and res.get("n_valid", 0) and optimise and int(res["status"][0]) in (1, 2):
+                th = np.asarray(res["theta"][0], dtype=np.float64)
+                if prev is not None and not np.isnan(th).any():
+                    prev = 0.95 * prev + 0.05 * th
+            if pieces:
+                for name, lst in pieces.items():
+                    pending.setdefault(name, []).extend(lst)
+                n_pending += 1
+                if n_pending >= store_every:
+                    flush()
+        if n_pending:
+            flush()
 
     @classmethod
     def run_from(cls, ref_oi, **run_kwargs):

@@ -224,6 +224,21 @@ def main():
         for sec, key in (("locations", "source"), ("data", "data_source"), ("pred_loc", "df_file")):
             c2[sec][key] = os.path.basename(c2[sec][key])
         json.dump(c2, f, indent=1)
+    # ---- scenario C: load_params={"previous": True} -- every expert starts from the EMA of its predecessors ----
+    cfg_c = copy.deepcopy(cfg)
+    cfg_c["results"]["file"] = "ABC_binned_oi_previous.h5"
+    cfg_c["model"]["load_params"] = {"previous": True}
+    store_c = os.path.join(cfg_c["results"]["dir"], cfg_c["results"]["file"])
+    oi = LocalExpertOI(expert_loc_config=copy.deepcopy(cfg_c["locations"]), data_config=copy.deepcopy(cfg_c["data"]),
+                       model_config=copy.deepcopy(cfg_c["model"]), pred_loc_config=copy.deepcopy(cfg_c["pred_loc"]))
+    oi.run(store_path=store_c, **dict(cfg_c["run_kwargs"], store_every=2))
+    dump_store(store_c, "scenario_c")
+    with open(os.path.join(OUT, "config_c.json"), "w") as f:
+        c2 = copy.deepcopy(cfg_c)
+        c2["results"]["dir"] = "."
+        for sec, key in (("locations", "source"), ("data", "data_source"), ("pred_loc", "df_file")):
+            c2[sec][key] = os.path.basename(c2[sec][key])
+        json.dump(c2, f, indent=1)
     fh.uninstall()
 
 

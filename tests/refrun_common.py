@@ -49,7 +49,7 @@ def setup_files(tmp, which="config.json", oi_model="B200GPRModel"):
     cfg["results"]["dir"] = tmp
     for sec, key in (("locations", "source"), ("data", "data_source"), ("pred_loc", "df_file")):
         cfg[sec][key] = os.path.join(tmp, cfg[sec][key])
-    if cfg["model"].get("load_params"):
+    if (cfg["model"].get("load_params") or {}).get("file"):
         cfg["model"]["load_params"]["file"] = os.path.join(tmp, cfg["model"]["load_params"]["file"])
     cfg["model"]["oi_model"] = oi_model
     return cfg, data, os.path.join(tmp, cfg["results"]["file"])

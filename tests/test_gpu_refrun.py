@@ -97,3 +97,27 @@ def test_run_from_a_configured_reference_instance(store):
     tabs = LocalExpertOI.run_from(ref_oi, store_path=None, optimise=True)
     want = {k: v for k, v in ref.items() if k not in ("oi_config", "expert_locs")}
     rc.compare_store({k: tabs[k] for k in want}, want, optimised=True, rtol_pred=1e-4)
+
+
+def test_previous_parameters_and_replacement_model_sequential_fallback(store):
+    """scenario C on the GPU (load_params={"previous": True}: EMA warm start, one expert per engine call), then a
+    replacement_threshold run: experts with fewer observations than the threshold get the replacement settings."""
+    from gpsat_b200.local_experts import LocalExpertOI
+    cfg, _, store_path = rc.setup_files(store, "config_c.json")
+    rc.make_oi(LocalExpertOI, cfg).run(store_path=store_path, **dict(cfg["run_kwargs"], store_every=2))
+    ref, app = rc.golden("scenario_c")
+    rc.compare_store(dict(fh.tables(store_path)), ref, optimised=True, rtol_pred=1e-4)
+    rc.compare_appends(fh.appends(store_path), app)
+    # replacement model: below 700 observations use tighter lengthscale bounds (a different optimum)
+    cfg2, _, _ = rc.setup_files(store)
+    cfg2["model"].update(replacement_threshold=700, replacement_model="B200GPRModel",
+                         replacement_constraints={"lengthscales": {"low": [1e-8] * 3, "high": [200000, 200000, 4]}})
+    tabs = rc.make_oi(LocalExpertOI, cfg2).run(store_path=None, optimise=True)
+    base = rc.golden("scenario_a")[0]
+    n = tabs["run_details"]["num_obs"].values[:5]
+    ls = tabs["lengthscales"]["lengthscales"].values.reshape(5, 3)
+    ls0 = base["lengthscales"]["lengthscales"].values.reshape(5, 3)
+    assert ((n < 700) == (ls[:, 2] <= 4.0 + 1e-9)).all(), (n, ls[:, 2])          # replaced experts obey the new bound
+    big = n >= 700
+    assert big.any() and (~big).any()
+    np.testing.assert_allclose(ls[big], ls0[big], rtol=2e-2)                      # the others are unchanged

@@ -165,6 +165,18 @@ def test_driver_predict_only_from_smoothed_tables(store, cpu_driver):
     rc.compare_appends(fh.appends(store_path), new)
 
 
+def test_driver_previous_parameters_sequential_fallback(store, cpu_driver):
+    """scenario C: load_params={"previous": True} makes experts order-dependent (EMA warm start,
+    local_experts.py:1079-1083,1200-1217): the driver falls back to one expert per engine call in list order and
+    flushes every store_every experts like the reference -- same tables, same appends."""
+    cfg, _, store_path = rc.setup_files(store, "config_c.json")
+    oi = rc.make_oi(cpu_driver.LocalExpertOI, cfg)
+    oi.run(store_path=store_path, **dict(cfg["run_kwargs"], store_every=2))
+    ref, app = rc.golden("scenario_c")
+    rc.compare_store(dict(fh.tables(store_path)), ref, optimised=True, rtol_pred=1e-4)
+    rc.compare_appends(fh.appends(store_path), app)
+
+
 def test_load_params_forms_and_missing_experts(store, cpu_driver):
     """an expert missing from the parameter tables is skipped (not a crash), NaN parameters fall back to the
     model default, fixed values can be given inline, and index_adjust shifts the lookup key."""
