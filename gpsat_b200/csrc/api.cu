@@ -68,6 +68,7 @@ struct gpsat_handle {
   bool attrs_set = false;
   int plan_slots = 0, plan_nbmax = 0;   // last make_plan (gpsat_last_plan)
   size_t plan_bytes_per_slot = 0;
+  bool safe_panel = false;       // Cholesky panels as two launches (GPSAT_SAFE_PANEL=1, or after a flag-wait timeout)
   int* timeouts_dev = nullptr;   // [1] flag-wait timeouts of k_potrf_panel (device counter, see GPSAT_ESYNC)
   long long timeouts_seen = 0;   // value already reported to the caller
 };
@@ -120,6 +121,7 @@ extern "C" int gpsat_create(gpsat_handle** out, int device, size_t mem_budget_by
   h->n_sm = prop.multiProcessorCount;
   if (const char* eg = getenv("GPSAT_GROUPS")) h->n_groups = std::max(1, std::min(MAX_GROUPS, atoi(eg)));
   if (const char* es = getenv("GPSAT_MAX_SLOTS")) h->max_slots = std::max(1, atoi(es));
+  if (const char* sp = getenv("GPSAT_SAFE_PANEL")) h->safe_panel = atoi(sp) != 0;
   size_t free_b = 0, total_b = 0;
   CK(cudaMemGetInfo(&free_b, &total_b));
   h->budget = mem_budget_bytes ? mem_budget_bytes : (size_t)(0.7 * (double)free_b);
@@ -185,6 +187,7 @@ static int check_sync_timeouts(gpsat_handle* h) {
   if (v > h->timeouts_seen) {
     const long long d = v - h->timeouts_seen;
     h->timeouts_seen = v;
+    h->safe_panel = true;      // in-order CTA dispatch did not hold on this device / under this tool: stop relying on it
     return fail(GPSAT_ESYNC, std::to_string(d) + " Cholesky panel CTA(s) timed out waiting for a diagonal block; the "
                              "affected evaluations were treated as non-positive-definite (f = +inf)");
   }
@@ -360,8 +363,18 @@ static int run_round_flags(gpsat_handle* h, const SlotCtx& c, int nbm, int flags
   }
   if (prof) cudaEventRecord(next_event(h), st);
   for (int J = 0; J < nsr; ++J) {
-    k_potrf_panel<<<c.S + c.S * (nsr - J - 1), NTHREADS, PANEL_SMEM_BYTES, st>>>(c, J, nsr);
-    ++h->launches;
+    const int n_off = c.S * (nsr - J - 1);
+    if (!h->safe_panel) {
+      k_potrf_panel<<<c.S + n_off, NTHREADS, PANEL_SMEM_BYTES, st>>>(c, J, nsr, 0);
+      ++h->launches;
+    } else {      // diagonal blocks complete (kernel boundary) before any block that waits for their flag starts
+      k_potrf_panel<<<c.S, NTHREADS, PANEL_SMEM_BYTES, st>>>(c, J, nsr, 0);
+      ++h->launches;
+      if (n_off > 0) {
+        k_potrf_panel<<<n_off, NTHREADS, PANEL_SMEM_BYTES, st>>>(c, J, nsr, c.S);
+        ++h->launches;
+      }
+    }
   }
   k_quad<<<c.S, NTHREADS, 0, st>>>(c);
   ++h->launches;

@@ -362,15 +362,20 @@ __device__ __forceinline__ void st_release_gpu(int* p, int v) {
   asm volatile("st.release.gpu.global.s32 [%0], %1;\n" ::"l"(p), "r"(v) : "memory");
 }
 
-__global__ void __launch_bounds__(NTHREADS, 1) k_potrf_panel(SlotCtx c, int J, int nsr_max) {
+// block0: index of this launch's first block in the panel's block numbering.  One launch covers the whole panel
+// (block0 = 0); the safe mode of the host (api.cu: after a flag-wait timeout, or GPSAT_SAFE_PANEL=1) launches the
+// diagonal blocks [0, S) and the off-diagonal blocks [S, ...) as two kernels, so that the flag is set before any waiter
+// exists and nothing depends on the order in which the hardware dispatches CTAs.
+__global__ void __launch_bounds__(NTHREADS, 1) k_potrf_panel(SlotCtx c, int J, int nsr_max, int block0) {
   extern __shared__ __align__(128) double smem[];
   __shared__ __align__(8) uint64_t xbar[2];
   int s, I;
-  if ((int)blockIdx.x < c.S) {
-    s = blockIdx.x;
+  const int bid = (int)blockIdx.x + block0;
+  if (bid < c.S) {
+    s = bid;
     I = J;
   } else {
-    const int b = blockIdx.x - c.S, nd = nsr_max - J - 1;
+    const int b = bid - c.S, nd = nsr_max - J - 1;
     s = b / nd;
     I = J + 1 + b % nd;
   }

@@ -600,3 +600,36 @@ def test_slot_groups_on_streams_are_bitwise_equivalent(eng):
     for k in res["1"]:
         np.testing.assert_array_equal(res["1"][k], res["3"][k], err_msg=k)
     assert (res["3"]["status"] > 0).all()
+
+
+def test_safe_panel_mode_is_bitwise_equivalent(eng):
+    """GPSAT_SAFE_PANEL=1 (also switched on by the library after a flag-wait timeout, GPSAT_ESYNC): the Cholesky panel runs
+    as two launches -- diagonal blocks, then the blocks that consume their flags -- so nothing depends on the order
+    in which CTAs are dispatched.  Same arithmetic, same results, and no timeouts on a healthy device either way."""
+    from gpsat_b200.engine import Engine
+    rng = np.random.default_rng(5)
+    sizes = [700, 130, 64, 300, 513]
+    Xs, zs = [], []
+    for n in sizes:
+        X, z, cs = _synth(rng, n)
+        Xs.append(X)
+        zs.append(z)
+    off, Xc, zc = _pack(Xs, zs)
+    theta = np.array([3.0, 2.5, 4.0, 0.02, 0.004])
+    out = {}
+    for mode in ("0", "1"):
+        os.environ["GPSAT_SAFE_PANEL"] = mode
+        e2 = Engine(0)
+        try:
+            b = e2.make_batch(off, Xc, zc, coords_scale=cs)
+            n0 = e2.launch_count()
+            f, g = e2.eval(b, theta, grad=True)
+            out[mode] = (f.cpu().numpy(), g.cpu().numpy(), e2.launch_count() - n0)
+            assert e2.sync_timeouts() == 0
+        finally:
+            e2.close()
+            os.environ.pop("GPSAT_SAFE_PANEL", None)
+    np.testing.assert_array_equal(out["0"][0], out["1"][0])
+    np.testing.assert_array_equal(out["0"][1], out["1"][1])
+    assert out["1"][2] > out["0"][2]          # the safe mode really took the two-launch path
+    assert eng.sync_timeouts() == 0
