@@ -277,11 +277,14 @@ def run_experts_host(eng: Engine, spec: ModelSpec, table, table_cols, obs_col, c
     return to_host(res, dev)
 
 
+_STAGING = {}     # device index -> grow-only pinned staging buffer (uint8)
+
+
 def to_host(res: dict, dev) -> dict:
-    """All device tensors of a result dict to numpy through ONE pinned buffer and ONE synchronisation (a ``.cpu()`` per
-    tensor is a pageable, synchronous copy each: the predict-only workload returns ~100 MB).  The returned arrays are
-    views of that buffer, which they keep alive; torch's caching host allocator recycles it once they are dropped, so
-    steady-state calls neither page-lock new memory nor copy a second time."""
+    """All device tensors of a result dict to numpy through one pinned staging buffer (a ``.cpu()`` per tensor is a
+    pageable, synchronous copy each: the predict-only workload returns ~100 MB).  The device->host copies are queued
+    back to back with an event after each; the host copies tensor k out of the staging buffer while tensor k+1 is
+    still in flight, so the second (pageable) copy hides behind the PCIe transfer."""
     items = [(k, v) for k, v in res.items() if isinstance(v, torch.Tensor) and v.is_cuda]
     out = {k: (v.numpy() if isinstance(v, torch.Tensor) else v) for k, v in res.items()
            if not (isinstance(v, torch.Tensor) and v.is_cuda)}
@@ -289,18 +292,23 @@ def to_host(res: dict, dev) -> dict:
         return out
     sizes = [((v.numel() * v.element_size() + 63) // 64) * 64 for _, v in items]
     total = max(sum(sizes), 64)
-    buf = torch.empty(total, dtype=torch.uint8, pin_memory=True)
-    off = 0
-    views = []
+    key = dev.index if hasattr(dev, "index") else int(dev)
+    buf = _STAGING.get(key)
+    if buf is None or buf.numel() < total:
+        buf = _STAGING[key] = torch.empty(total + total // 4, dtype=torch.uint8, pin_memory=True)
+    stream = torch.cuda.current_stream(dev)
+    off, staged = 0, []
     for (k, v), sz in zip(items, sizes):
         nbytes = v.numel() * v.element_size()
         dst = buf[off:off + nbytes].view(v.dtype).reshape(v.shape)
         dst.copy_(v.contiguous(), non_blocking=True)
-        views.append((k, dst))
+        ev = torch.cuda.Event()
+        ev.record(stream)
+        staged.append((k, dst, ev))
         off += sz
-    torch.cuda.current_stream(dev).synchronize()
-    for k, dst in views:
-        out[k] = dst.numpy()
+    for k, dst, ev in staged:
+        ev.synchronize()
+        out[k] = dst.numpy().copy()          # the staging buffer is reused by the next call
     return out
 
 

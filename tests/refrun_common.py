@@ -82,7 +82,7 @@ def compare_structure(got: pd.DataFrame, ref: pd.DataFrame, name):
             assert (g[c].values == r[c].values).all(), (name, c)
 
 
-def compare_store(got, ref, optimised, rtol_pred, lml_slack=1e-6, suffix=""):
+def compare_store(got, ref, optimised, rtol_pred, lml_slack=1e-6, suffix="", rtol_var=None):
     """got / ref: {table: DataFrame}.  Structure, order and integer / index content exactly; floats per BASELINE.json."""
     assert set(got) == set(ref), (sorted(got), sorted(ref))
     for name in ref:
@@ -102,8 +102,9 @@ def compare_store(got, ref, optimised, rtol_pred, lml_slack=1e-6, suffix=""):
     ends = np.r_[starts[1:], len(pr)]
     for c in ("f*", "f*_var", "y_var"):
         a, b = p[c].values, pr[c].values
+        tol = rtol_pred if (c == "f*" or rtol_var is None) else rtol_var
         for s, e in zip(starts, ends):
-            np.testing.assert_allclose(a[s:e], b[s:e], rtol=rtol_pred, atol=rtol_pred * np.abs(b[s:e]).max(),
+            np.testing.assert_allclose(a[s:e], b[s:e], rtol=tol, atol=tol * np.abs(b[s:e]).max(),
                                        err_msg=f"preds.{c}")
     for nm in HYPERS:
         if f"{nm}{suffix}" in ref and f"{nm}{suffix}" in got:
