@@ -611,10 +611,15 @@ extern "C" int gpsat_gpr_optimise(gpsat_handle* h, const gpsat_batch* b, const d
           if (r) return r;
         }
       }
-      if (trace)
-        fprintf(trace, "%lld,%d,%.1f,%d,%d,%.4g\n", q.rounds, g,
+      if (trace) {
+        // dry = 1: the group's previous round had already finished when this one was queued, i.e. its stream ran out
+        // of work and waited for the host (with the one-round look-ahead this should be rare)
+        const int dry = (q.rounds > 0 &&
+                         cudaEventQuery(h->gevent2[g][(q.rounds - 1) & 1]) == cudaSuccess) ? 1 : 0;
+        fprintf(trace, "%lld,%d,%.1f,%d,%d,%.4g,%d\n", q.rounds, g,
                 std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - t_trace0).count(),
-                q.nact, q.nbm, q.fl);
+                q.nact, q.nbm, q.fl, dry);
+      }
       if (q.nact == 0) {
         q.done = true;
         --live;
