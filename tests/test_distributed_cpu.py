@@ -101,3 +101,57 @@ def test_pack_unpack_round_trip_including_empty_shards():
             if res["n_valid"] == 0 and k not in ("num_obs", "has_pred", "too_few", "valid", "n_valid", "valid_idx"):
                 continue
             np.testing.assert_array_equal(np.asarray(back[k]).reshape(np.asarray(v).shape), np.asarray(v), err_msg=k)
+
+
+def _driver_worker(rank, world, port, tmp, q):
+    """LocalExpertOI.run under torch.distributed (gloo): rank 0 alone reads / writes the store, the others follow its
+    config id and resume decisions.  The engine call is the oracle-backed stand-in of tests/refrun_common.py."""
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    # two processes share this container's cores: BLAS pools (numpy's, and scipy's, which loads later) spin when
+    # oversubscribed, so both are capped before and after the imports
+    os.environ["OPENBLAS_NUM_THREADS"] = os.environ["OMP_NUM_THREADS"] = "2"
+    from threadpoolctl import threadpool_limits
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        import gpsat_b200
+        import refrun_common as rc
+        import scipy.linalg  # noqa: F401
+        from gpsat_b200 import local_experts as le
+        threadpool_limits(limits=2)
+        rc.fh.install()
+        le.run_experts_sharded = rc.oracle_backed_sharded
+        gpsat_b200.get_engine = lambda device=0: None
+        le.LocalExpertOI._device_name = lambda self: "oracle-cpu"
+        cfg, _, store_path = rc.setup_files(os.path.join(tmp, f"rank{rank}"))
+        oi = rc.make_oi(le.LocalExpertOI, cfg)
+        oi.expert_locs = oi.expert_locs.iloc[[0, 1, 5]].copy(True)       # two ordinary experts + the one without data
+        tabs = oi.run(store_path=store_path, return_tables=True, **dict(cfg["run_kwargs"], max_batch=8))
+        wrote = sorted(rc.fh.tables(store_path)) if os.path.abspath(store_path) in rc.fh.FILES else []
+        q.put((rank, sorted(tabs), len(tabs["run_details"]), wrote))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_driver_run_under_two_ranks_only_rank0_touches_the_store(tmp_path):
+    for r in range(2):
+        os.makedirs(tmp_path / f"rank{r}")
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_driver_worker, args=(r, 2, port, str(tmp_path), q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got = dict((r[0], r[1:]) for r in (q.get(timeout=300), q.get(timeout=300)))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    # both ranks shaped the same tables (3 locations: 2 ran + 1 with too few observations) ...
+    assert got[0][0] == got[1][0] and got[0][1] == got[1][1] == 3
+    # ... but only rank 0 wrote them (rank 1's store holds nothing but the input table it was seeded with)
+    assert "run_details" in got[0][2] and "oi_config" in got[0][2] and "expert_locs" in got[0][2]
+    assert got[1][2] == []
