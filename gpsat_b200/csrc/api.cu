@@ -593,10 +593,18 @@ extern "C" int gpsat_gpr_optimise(gpsat_handle* h, const gpsat_batch* b, const d
     }
     return 0;
   };
-  for (long long round = 0; round < max_rounds && live > 0; ++round) {
+  // The host never blocks on ONE group's census while another group's stream could be fed: a census that is not
+  // ready yet is skipped in this pass (cudaEventQuery); only when no group made progress does the host wait -- on the
+  // oldest outstanding census, which is the next thing that can unblock anything.
+  bool limit_hit = false;
+  while (live > 0 && !limit_hit) {
+    bool progressed = false;
+    int wait_g = -1;
+    long long wait_c = 0;
     for (int g = 0; g < G; ++g) {
       Group& q = grp[g];
       if (q.done) continue;
+      if (q.rounds >= max_rounds) { limit_hit = true; break; }
       cudaStream_t sg = (G == 1) ? st : h->gstream[g];
       // census index -1 = the slot table after k_slot_init; census c >= 0 = the table after round c
       if (q.rounds == 0) {
@@ -607,10 +615,15 @@ extern "C" int gpsat_gpr_optimise(gpsat_handle* h, const gpsat_batch* b, const d
       } else {
         const long long c = q.rounds - 1 - lookahead;
         if (c >= 0) {
+          if (G > 1 && cudaEventQuery(h->gevent2[g][c & 1]) == cudaErrorNotReady) {
+            if (wait_g < 0) { wait_g = g; wait_c = c; }
+            continue;                         // feed the other groups first
+          }
           r = read_census(g, c);
           if (r) return r;
         }
       }
+      progressed = true;
       if (trace) {
         // dry = 1: the group's previous round had already finished when this one was queued, i.e. its stream ran out
         // of work and waited for the host (with the one-round look-ahead this should be rare)
@@ -634,6 +647,7 @@ extern "C" int gpsat_gpr_optimise(gpsat_handle* h, const gpsat_batch* b, const d
       ++q.rounds;
       if (h->profiling && h->ev_used > 4000) { CK(cudaStreamSynchronize(sg)); harvest_profile(h, true, true); }
     }
+    if (!progressed && !limit_hit && wait_g >= 0) CK(cudaEventSynchronize(h->gevent2[wait_g][wait_c & 1]));
   }
   if (G > 1) {
     for (int g = 0; g < G; ++g) {

@@ -19,8 +19,10 @@ one = [x for x in items if x["s"] == items[0]["s"]]
 i0 = [i for i, x in enumerate(one) if x["k"].startswith("k_build")][0]
 B = "sm__pipe_tensor_subpipe_dmma_cycles_active.avg.pct_of_peak_sustained_elapsed"
 print(f"# {tag}: one objective evaluation (\"round\") of one slot group, launch by launch\n")
-print("`bash profiles/run_ncu3.sh` = `ncu --metrics gpu__time_duration.sum," + B + ",dram__bytes_read.sum,"
-      "dram__bytes_write.sum --clock-control none` on `python bench.py --experts-per-step 592 --steps 1 --warmup 1` "
+script, cmd = ("profiles/capture_r02.sh (pass 2)", "python bench.py --steps 1 --warmup 1 --no-cpu-baseline --skip-e2e") \
+    if tag.startswith("r02") else ("profiles/run_ncu3.sh", "python bench.py --experts-per-step 592 --steps 1 --warmup 1")
+print(f"`bash {script}` = `ncu --metrics gpu__time_duration.sum," + B + ",dram__bytes_read.sum,"
+      f"dram__bytes_write.sum --clock-control none` on `{cmd}` "
       "(c3 workload; launches serialised by ncu, cold caches).\n")
 print("| kernel | grid | time (us) | DMMA pipe busy (% of elapsed) | DRAM read+write (MB) |\n|---|---|---|---|---|")
 tot = collections.OrderedDict()
