@@ -354,7 +354,7 @@ def run_b200(args):
     eng.set_profiling(True)
     pe0, pe1 = torch.cuda.Event(True), torch.cuda.Event(True)
     pe0.record()
-    idx = list_idx(args.warmup + args.steps - 1)[rank::world][:B]
+    idx = list_idx(args.warmup + args.steps - 1)[rank::world][:min(B, 1024)]
     run_experts(eng, spec, table_d, refs_dev=torch.from_numpy(np.ascontiguousarray(w["experts"][idx])).to(dev),
                 pred_table_dev=pred_d, theta_init=None if theta_all is None else np.ascontiguousarray(theta_all[idx]),
                 **kw)
