@@ -404,8 +404,10 @@ def run_b200(args):
                 "achieved": phases[dom]["tflops"], "peak": peak, "unit": "TFLOP/s",
                 "frac": (phases[dom]["tflops"] / peak) if phases[dom]["tflops"] else None,
                 "traffic": None if traffic is None else traffic.get(dom, {}).get("dram_bytes_per_launch"),
-                "traffic_note": ("dram__bytes_read.sum + dram__bytes_write.sum per launch of the phase's dominant kernel "
-                                 "from the ncu --set full capture of this batch configuration: " +
+                "traffic_note": ("dram__bytes_read.sum + dram__bytes_write.sum per launch of the phase's dominant kernel, "
+                                 "averaged over every launch of it in one round, from the ncu captures of this batch "
+                                 "configuration (profiles/capture_r02.sh -> profiles/r02_traffic.json; the --set full "
+                                 "figures of three of the launches are under full_set_capture): " +
                                  json.dumps(traffic.get(dom))) if traffic else
                                 "null: no ncu --set full capture of this batch configuration is committed "
                                 "(profiles/r02_traffic.json)",
