@@ -39,8 +39,10 @@ struct Acc2 {
 struct Frag2 {
   static constexpr bool kHalves = false;   // every warp owns all 64 rows of its slab
   int lane, warp, q, r, ta, tb, nb0;
-  __device__ __forceinline__ int mi_begin() const { return 0; }
+  __device__ __forceinline__ int mi_begin() const { return 0; }     // 8-row groups this warp COMPUTES ...
   __device__ __forceinline__ int mi_end() const { return 8; }
+  __device__ __forceinline__ int st_begin() const { return 0; }     // ... and STORES
+  __device__ __forceinline__ int st_end() const { return 8; }
   __device__ __forceinline__ Frag2() {
     lane = threadIdx.x & 31;
     warp = threadIdx.x >> 5;
@@ -56,6 +58,22 @@ struct Frag2 {
   }
   __device__ __forceinline__ int row(int mi) const { return 8 * mi + q; }             // within tile ta
   __device__ __forceinline__ int col(int ni) const { return nb0 + 8 * ni + 2 * r; }   // within tile tb (and col+1)
+};
+
+// Frag2 with row skipping: a warp whose tile is the LAST tile row of the matrix computes only rows 0-31 of its slab when
+// rows 32-63 of that tile are padding (their results are structural zeros).  `last_tile` = index of the last tile
+// row (nb - 1), `tile0` = tile row of ta = 0, `half_pad` = rows 32-63 of the last tile are all padding.
+struct Frag2H : Frag2 {
+  static constexpr bool kHalves = true;
+  int half;
+  __device__ __forceinline__ Frag2H(int tile0, int last_tile, bool half_pad) : Frag2() {
+    half = (half_pad && tile0 + ta == last_tile) ? 1 : 0;
+  }
+  __device__ __forceinline__ int mi_begin() const { return 0; }
+  __device__ __forceinline__ int mi_end() const { return half == 1 ? 4 : 8; }
+  // the skipped rows are still stored (as the zeros the accumulators were cleared to): later kernels read whole tiles
+  __device__ __forceinline__ int st_begin() const { return 0; }
+  __device__ __forceinline__ int st_end() const { return 8; }
 };
 
 // Warp map for DIAGONAL supertiles (output = tiles (0,0), (1,0), (1,1); tile (0,1) is the mirror image of (1,0) and
@@ -89,6 +107,8 @@ struct Frag2D {
   }
   __device__ __forceinline__ int mi_begin() const { return half == 2 ? 4 : 0; }
   __device__ __forceinline__ int mi_end() const { return half == 1 ? 4 : 8; }
+  __device__ __forceinline__ int st_begin() const { return mi_begin(); }   // the other half belongs to another warp
+  __device__ __forceinline__ int st_end() const { return mi_end(); }
   __device__ __forceinline__ int row(int mi) const { return 8 * mi + q; }
   __device__ __forceinline__ int col(int ni) const { return nb0 + 8 * ni + 2 * r; }
 };
@@ -226,8 +246,10 @@ struct NoTail {
 // before the ring is reused.
 template <bool TA, bool TBm, bool TAIL, class FA, class FB, class FRAG, class FT>
 __device__ __forceinline__ void gemm2_pipeline_t(Acc2& acc, double* smem, G2Pipe& p, int kbeg, int kend, FA a_of,
-                                                 FB b_of, const FRAG& f, FT tail_of, const double** tail) {
-  const int nsl = (kend > kbeg) ? 2 * (kend - kbeg) : 0;   // 32-deep slices
+                                                 FB b_of, const FRAG& f, FT tail_of, const double** tail,
+                                                 int drop_last = 0) {
+  // drop_last = 1: the second 32-deep half of the LAST k-tile holds only padding (structural zeros) and is not streamed
+  const int nsl = (kend > kbeg) ? 2 * (kend - kbeg) - drop_last : 0;   // 32-deep slices
   const int ntot = nsl + (TAIL ? 2 : 0);
   if (ntot == 0) return;
   auto issue = [&](int sl) {    // one thread
@@ -294,15 +316,15 @@ __device__ __forceinline__ void gemm2_pipeline_t(Acc2& acc, double* smem, G2Pipe
 
 template <bool TA, bool TBm, class FA, class FB, class FRAG>
 __device__ __forceinline__ void gemm2_pipeline(Acc2& acc, double* smem, G2Pipe& p, int kbeg, int kend, FA a_of,
-                                               FB b_of, const FRAG& f) {
-  gemm2_pipeline_t<TA, TBm, false>(acc, smem, p, kbeg, kend, a_of, b_of, f, NoTail(), nullptr);
+                                               FB b_of, const FRAG& f, int drop_last = 0) {
+  gemm2_pipeline_t<TA, TBm, false>(acc, smem, p, kbeg, kend, a_of, b_of, f, NoTail(), nullptr, drop_last);
 }
 
 // store this warp's 64x32 slab into a swizzled 64x64 tile (global or shared), scaled
 template <class FRAG>
 __device__ __forceinline__ void store_acc2(double* __restrict__ tile, const Acc2& acc, const FRAG& f,
                                            double scale = 1.0) {
-  const int m0 = f.mi_begin(), m1 = f.mi_end();
+  const int m0 = f.st_begin(), m1 = f.st_end();
 #pragma unroll
   for (int mi = 0; mi < 8; ++mi) {
     if (mi < m0 || mi >= m1) continue;      // rows this warp does not own (Frag2D half slabs)

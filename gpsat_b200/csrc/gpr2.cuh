@@ -402,7 +402,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_potrf_panel(SlotCtx c, int J, i
   };
   if (I != J) {
     // ---- off-diagonal supertile: C = K - sum_k L_Ik L_Jk', then L_I,panel = C X_JJ' ----
-    Frag2 f;
+    // (rows 32-63 of the last tile row are skipped when they are all padding: their C and L entries are exact zeros)
+    Frag2H f(2 * I, nb - 1, (N - (nb - 1) * TB) < 32);
     // L_I,panel = [C0 C1] X_JJ' with X_JJ = [[X00, 0], [X10, X11]]:  column j0 = C0 X00',  column j1 = C0 X10' + C1 X11'.
     // Step 1 (k = j1, column-j1 warps only) needs X11 alone: it is fetched early into the extra tile behind the ring,
     // and X00 / X10 for step 2 land in the third ring slot while step 1 runs.
@@ -573,7 +574,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_trtri_pass1(SlotCtx c, int h) {
   if (!trtri_decode(blockIdx.x, h, nsr, P, Q, mid)) return;
   double* Lt = c.Lt + (long)s * c.tile_stride;
   double* Xt = c.Xt + (long)s * c.tile_stride;
-  Frag2 f;
+  Frag2H f(2 * P, nb - 1, (c.n[s] - (nb - 1) * TB) < 32);     // padded rows of the last tile row are not computed
   G2Pipe pipe;
   pipe.init();
   Acc2 acc;
@@ -596,7 +597,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_trtri_pass2(SlotCtx c, int h) {
   if (!trtri_decode(blockIdx.x, h, nsr, P, Q, mid)) return;
   double* Lt = c.Lt + (long)s * c.tile_stride;
   double* Xt = c.Xt + (long)s * c.tile_stride;
-  Frag2 f;
+  Frag2H f(2 * P, nb - 1, (c.n[s] - (nb - 1) * TB) < 32);
   G2Pipe pipe;
   pipe.init();
   Acc2 acc;
@@ -616,7 +617,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_trtri_pass2(SlotCtx c, int h) {
 __global__ void __launch_bounds__(NTHREADS, 1) k_lauum2(SlotCtx c) {
   extern __shared__ __align__(128) double smem[];
   const int s = blockIdx.y;
-  const int act = c.active[s], nb = c.nb[s];
+  const int act = c.active[s], nb = c.nb[s], N = c.n[s];
   if (!act) return;
   const int nsr = (nb + 1) >> 1;
   int I, J;
@@ -633,15 +634,18 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_lauum2(SlotCtx c) {
   auto b_of = [&](int k, int t) -> const double* {
     return (2 * J + t < nb && k >= 2 * J + t) ? x_tile(c, s, k, 2 * J + t) : nullptr;
   };
+  // rows N+1 .. 64 nb - 1 of X are identity padding: when they fill the second half of the last k-tile that slice adds
+  // nothing to any entry the gradient reads, and it is not streamed (every task's k-loop ends with it)
+  const int drop = ((N - (nb - 1) * TB) < 32) ? 1 : 0;
   if (I == J) {      // diagonal supertile: three tiles, balanced warp map (3/4 of a full supertile's time per k-step)
     Frag2D f;
-    gemm2_pipeline<true, true>(acc, smem, pipe, 2 * I, nb, a_of, b_of, f);
+    gemm2_pipeline<true, true>(acc, smem, pipe, 2 * I, nb, a_of, b_of, f, drop);
     const int ti = 2 * I + f.ta, tj = 2 * J + f.tb;
     if (ti < nb && tj < nb) store_acc2(tile_ptr(Kt, ti, tj), acc, f);
     return;
   }
   Frag2 f;
-  gemm2_pipeline<true, true>(acc, smem, pipe, 2 * I, nb, a_of, b_of, f);
+  gemm2_pipeline<true, true>(acc, smem, pipe, 2 * I, nb, a_of, b_of, f, drop);
   const int ti = 2 * I + f.ta, tj = 2 * J + f.tb;
   if (ti < nb && tj < nb && tj <= ti) store_acc2(tile_ptr(Kt, ti, tj), acc, f);
 }
