@@ -182,16 +182,28 @@ __device__ __forceinline__ void mma_half_r(Acc2& acc, const double* __restrict__
     }
   }
 }
-template <bool TA, bool TBm, class FRAG, class HOOK>
-__device__ __forceinline__ void mma_half_h(Acc2& acc, const double* __restrict__ As, const double* __restrict__ Bs,
-                                           const FRAG& f, HOOK last_loads_done) {
-  if constexpr (FRAG::kHalves) {      // warp-uniform
-    if (f.half == 0) mma_half_r<TA, TBm, 0, 8>(acc, As, Bs, f, last_loads_done);
-    else if (f.half == 1) mma_half_r<TA, TBm, 0, 4>(acc, As, Bs, f, last_loads_done);
+// rows: 0 = the whole slab, 1 = rows 0-31 (mi 0..3), 2 = rows 32-63 (mi 4..7); warp-uniform.  DYN = false compiles the
+// full-slab variant only.
+template <bool TA, bool TBm, bool DYN, class FRAG, class HOOK>
+__device__ __forceinline__ void mma_half_sel(Acc2& acc, const double* __restrict__ As, const double* __restrict__ Bs,
+                                             const FRAG& f, int rows, HOOK last_loads_done) {
+  if constexpr (DYN) {
+    if (rows == 0) mma_half_r<TA, TBm, 0, 8>(acc, As, Bs, f, last_loads_done);
+    else if (rows == 1) mma_half_r<TA, TBm, 0, 4>(acc, As, Bs, f, last_loads_done);
     else mma_half_r<TA, TBm, 4, 8>(acc, As, Bs, f, last_loads_done);
   } else {
     mma_half_r<TA, TBm, 0, 8>(acc, As, Bs, f, last_loads_done);
   }
+}
+template <class FRAG>
+__device__ __forceinline__ int own_rows(const FRAG& f) {
+  if constexpr (FRAG::kHalves) return f.half;
+  else return 0;
+}
+template <bool TA, bool TBm, class FRAG, class HOOK>
+__device__ __forceinline__ void mma_half_h(Acc2& acc, const double* __restrict__ As, const double* __restrict__ Bs,
+                                           const FRAG& f, HOOK last_loads_done) {
+  mma_half_sel<TA, TBm, FRAG::kHalves>(acc, As, Bs, f, own_rows(f), last_loads_done);
 }
 template <bool TA, bool TBm, class FRAG>
 __device__ __forceinline__ void mma_half(Acc2& acc, const double* __restrict__ As, const double* __restrict__ Bs,
@@ -230,6 +242,21 @@ struct G2Pipe {
 struct NoTail {
   __device__ __forceinline__ const double* operator()(int, int) const { return nullptr; }
 };
+// Row selector of a pipeline: rows_of(k, kh, ta) says which rows of the A-side tile `ta` can receive a non-zero
+// contribution from the 32-deep slice kh of k-tile k (0 = all, 1 = rows 0-31 only, 2 = rows 32-63 only) -- the slices
+// of TRIANGULAR operand tiles that are half zeros.  The rest of the slab is not multiplied.
+struct AllRows {
+  static constexpr bool kAll = true;
+  __device__ __forceinline__ int operator()(int, int, int) const { return 0; }
+};
+// the A-side tile `ta` is the lower-triangular DIAGONAL tile at k == d0 + ta: its slice `kh` reaches only `rows`
+struct DiagRows {
+  static constexpr bool kAll = false;
+  int d0, kh, rows;
+  __device__ __forceinline__ int operator()(int k, int kh_, int ta) const {
+    return (k == d0 + ta && kh_ == kh) ? rows : 0;
+  }
+};
 
 // acc += sum_{k = kbeg}^{kend-1} [A_k^0; A_k^1] * [B_k^0  B_k^1]  over 64-deep tile steps.
 // a_of(k, t) / b_of(k, t), t in {0,1}: global pointer of the tile or nullptr (structurally zero /
@@ -244,10 +271,10 @@ struct NoTail {
 // tail[e] (tile t at tail[e] + t * TILE_ELEMS, missing tiles are not touched).  Without TAIL the call ends with
 // every copy consumed and a __syncthreads(); with TAIL the caller reads the tiles and then must __syncthreads()
 // before the ring is reused.
-template <bool TA, bool TBm, bool TAIL, class FA, class FB, class FRAG, class FT>
+template <bool TA, bool TBm, bool TAIL, class FA, class FB, class FRAG, class FT, class ROWS = AllRows>
 __device__ __forceinline__ void gemm2_pipeline_t(Acc2& acc, double* smem, G2Pipe& p, int kbeg, int kend, FA a_of,
                                                  FB b_of, const FRAG& f, FT tail_of, const double** tail,
-                                                 int drop_last = 0) {
+                                                 int drop_last = 0, ROWS rows_of = ROWS()) {
   // drop_last = 1: the second 32-deep half of the LAST k-tile holds only padding (structural zeros) and is not streamed
   const int nsl = (kend > kbeg) ? 2 * (kend - kbeg) - drop_last : 0;   // 32-deep slices
   const int ntot = nsl + (TAIL ? 2 : 0);
@@ -286,13 +313,24 @@ __device__ __forceinline__ void gemm2_pipeline_t(Acc2& acc, double* smem, G2Pipe
     const bool refill = sl + G2_STAGES < ntot;
     int* cnt = p.done + p.stage(n);
     int seen = -1;                      // lane 0: the slot counter before this warp's release
-    if (a_of(k, f.ta) != nullptr && b_of(k, f.tb) != nullptr) {
+    // rows of this warp's slab that the slice can contribute to: the warp's own share, cut by the operand's structure
+    int rows = own_rows(f);
+    bool none = false;
+    if constexpr (!ROWS::kAll) {
+      const int sel = rows_of(k, sl & 1, f.ta);
+      if (sel != 0) {
+        if (rows == 0) rows = sel;
+        else if (rows != sel) none = true;
+      }
+    }
+    if (!none && a_of(k, f.ta) != nullptr && b_of(k, f.tb) != nullptr) {
       const double* st = smem + p.stage(n) * G2_STAGE_ELEMS;
       // the slot is released from inside the last k-step (its operands are in registers by then), so the latency of
       // the shared-memory atomic hides behind that step's 32 DMMAs instead of idling the pipe at the slice boundary
-      mma_half_h<TA, TBm>(acc, st + f.ta * HALF_ELEMS, st + (2 + f.tb) * HALF_ELEMS, f, [&]() {
-        if (refill && f.lane == 0) seen = atomicAdd(cnt, 1);
-      });
+      mma_half_sel<TA, TBm, (FRAG::kHalves || !ROWS::kAll)>(
+          acc, st + f.ta * HALF_ELEMS, st + (2 + f.tb) * HALF_ELEMS, f, rows, [&]() {
+            if (refill && f.lane == 0) seen = atomicAdd(cnt, 1);
+          });
     } else if (refill && f.lane == 0) {
       seen = atomicAdd(cnt, 1);
     }
@@ -314,10 +352,10 @@ __device__ __forceinline__ void gemm2_pipeline_t(Acc2& acc, double* smem, G2Pipe
   p.count += ntot;
 }
 
-template <bool TA, bool TBm, class FA, class FB, class FRAG>
+template <bool TA, bool TBm, class FA, class FB, class FRAG, class ROWS = AllRows>
 __device__ __forceinline__ void gemm2_pipeline(Acc2& acc, double* smem, G2Pipe& p, int kbeg, int kend, FA a_of,
-                                               FB b_of, const FRAG& f, int drop_last = 0) {
-  gemm2_pipeline_t<TA, TBm, false>(acc, smem, p, kbeg, kend, a_of, b_of, f, NoTail(), nullptr, drop_last);
+                                               FB b_of, const FRAG& f, int drop_last = 0, ROWS rows_of = ROWS()) {
+  gemm2_pipeline_t<TA, TBm, false>(acc, smem, p, kbeg, kend, a_of, b_of, f, NoTail(), nullptr, drop_last, rows_of);
 }
 
 // store this warp's 64x32 slab into a swizzled 64x64 tile (global or shared), scaled

@@ -603,12 +603,15 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_trtri_pass2(SlotCtx c, int h) {
   Acc2 acc;
   acc.zero();
   const int kend = (2 * P + 2 < nb) ? 2 * P + 2 : nb;
+  // the A operand of the last k-tile(s) is the lower-TRIANGULAR diagonal tile X[2P+ta, 2P+ta]: its columns 32-63
+  // (slice 1) are zero in rows 0-31
+  const DiagRows rows{2 * P, 1, 2};
   gemm2_pipeline<false, true>(
       acc, smem, pipe, 2 * mid, kend,
       [&](int k, int t) -> const double* {
         return (2 * P + t < nb && k <= 2 * P + t) ? x_tile(c, s, 2 * P + t, k) : nullptr;
       },
-      [&](int k, int t) -> const double* { return tile_ptr(Xt, k, 2 * Q + t); }, f);
+      [&](int k, int t) -> const double* { return tile_ptr(Xt, k, 2 * Q + t); }, f, 0, rows);
   const int ti = 2 * P + f.ta, tj = 2 * Q + f.tb;
   if (ti < nb) store_acc2(tile_ptr(Lt, ti, tj), acc, f, -1.0);
 }
@@ -637,15 +640,18 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_lauum2(SlotCtx c) {
   // rows N+1 .. 64 nb - 1 of X are identity padding: when they fill the second half of the last k-tile that slice adds
   // nothing to any entry the gradient reads, and it is not streamed (every task's k-loop ends with it)
   const int drop = ((N - (nb - 1) * TB) < 32) ? 1 : 0;
+  // the A operand of the first k-tile(s) is the lower-TRIANGULAR diagonal tile X[2I+ta, 2I+ta] used transposed: its rows
+  // 0-31 (slice 0) reach output rows 0-31 only
+  const DiagRows rows{2 * I, 0, 1};
   if (I == J) {      // diagonal supertile: three tiles, balanced warp map (3/4 of a full supertile's time per k-step)
     Frag2D f;
-    gemm2_pipeline<true, true>(acc, smem, pipe, 2 * I, nb, a_of, b_of, f, drop);
+    gemm2_pipeline<true, true>(acc, smem, pipe, 2 * I, nb, a_of, b_of, f, drop, rows);
     const int ti = 2 * I + f.ta, tj = 2 * J + f.tb;
     if (ti < nb && tj < nb) store_acc2(tile_ptr(Kt, ti, tj), acc, f);
     return;
   }
   Frag2 f;
-  gemm2_pipeline<true, true>(acc, smem, pipe, 2 * I, nb, a_of, b_of, f, drop);
+  gemm2_pipeline<true, true>(acc, smem, pipe, 2 * I, nb, a_of, b_of, f, drop, rows);
   const int ti = 2 * I + f.ta, tj = 2 * J + f.tb;
   if (ti < nb && tj < nb && tj <= ti) store_acc2(tile_ptr(Kt, ti, tj), acc, f);
 }
@@ -853,7 +859,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_predict2(SlotCtx c, PredCtx p) 
         [&](int k, int t) -> const double* {
           return (t == 0 || two) ? scr + ((long)k * 2 + t) * TILE_ELEMS : nullptr;
         },
-        f);
+        f, 0, DiagRows{2 * I, 1, 2});     // columns 32-63 of the triangular tile X[2I+t, 2I+t] reach rows 32-63 only
     const int ti = 2 * I + f.ta;
     if (STORE_A && ti < nb) {   // rows >= N (augmented row, padding) must not enter A'A
       Acc2 az = acc;
