@@ -861,16 +861,6 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_predict2(SlotCtx c, PredCtx p) 
         },
         f, 0, DiagRows{2 * I, 1, 2});     // columns 32-63 of the triangular tile X[2I+t, 2I+t] reach rows 32-63 only
     const int ti = 2 * I + f.ta;
-    if (STORE_A && ti < nb) {   // rows >= N (augmented row, padding) must not enter A'A
-      Acc2 az = acc;
-#pragma unroll
-      for (int mi = 0; mi < 8; ++mi)
-        if (ti * TB + f.row(mi) >= N || !(f.tb == 0 || two)) {
-#pragma unroll
-          for (int ni = 0; ni < 4; ++ni) az.c[mi][ni][0] = az.c[mi][ni][1] = 0.0;
-        }
-      store_acc2(p.abuf + (((long)blockIdx.x * c.nbmax + ti) * 2 + f.tb) * TILE_ELEMS, az, f);
-    }
     if (ti < nb && (f.tb == 0 || two)) {
 #pragma unroll
       for (int mi = 0; mi < 8; ++mi) {
@@ -886,6 +876,15 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_predict2(SlotCtx c, PredCtx p) 
           }
         }
       }
+    }
+    if (STORE_A && ti < nb) {   // rows >= N (augmented row, padding) must not enter A'A: zeroed in place, then stored
+#pragma unroll
+      for (int mi = 0; mi < 8; ++mi)
+        if (ti * TB + f.row(mi) >= N || !(f.tb == 0 || two)) {
+#pragma unroll
+          for (int ni = 0; ni < 4; ++ni) acc.c[mi][ni][0] = acc.c[mi][ni][1] = 0.0;
+        }
+      store_acc2(p.abuf + (((long)blockIdx.x * c.nbmax + ti) * 2 + f.tb) * TILE_ELEMS, acc, f);
     }
   }
   // column sums: over q (lanes sharing r), then over the two warps (ta = 0, 1) of a column slab
