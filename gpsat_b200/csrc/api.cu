@@ -36,6 +36,13 @@ static int fail(int code, const std::string& msg) {
 
 constexpr int MAX_GROUPS = 8;
 constexpr int MIN_GROUP_SLOTS = 32;
+// Look-ahead Cholesky panels for rounds of at most this many 128-row supertile rows (N <= 767), with LA_GROUPS slot
+// groups instead of 3.  Measured (profiles/r02_results.md): on c1 (N 400-640) the fused one-launch panels lose
+// throughput as slot groups are added (CTAs spinning on a diagonal block hold an SM: 1657 / 1619 / 1587 experts/s at
+// 3 / 6 / 8 groups) while the look-ahead panels gain (1722 / 1766 / 1764); c2 and c5 are unchanged; on c3 / c4 sizes
+// the two modes are equal within noise and the fused mode stays (its single-stream phase timing is 2 % better).
+constexpr int LA_MAX_NSR = 6;
+constexpr int LA_GROUPS = 6;
 
 struct Buf {
   void* p = nullptr;
@@ -60,6 +67,7 @@ struct gpsat_handle {
   size_t host_ints_cap = 0;
   int max_slots = 0;         // 0: 4 slots per SM (GPSAT_MAX_SLOTS overrides)
   int n_groups = 3;          // slot groups / streams of the optimiser (GPSAT_GROUPS overrides)
+  bool n_groups_env = false; // GPSAT_GROUPS was given: no automatic choice
   cudaStream_t gstream[8] = {};
   cudaEvent_t gevent[8] = {};
   cudaEvent_t gevent2[8][2] = {};   // census events of the optimiser rounds, [group][parity]
@@ -69,6 +77,7 @@ struct gpsat_handle {
   int plan_slots = 0, plan_nbmax = 0;   // last make_plan (gpsat_last_plan)
   size_t plan_bytes_per_slot = 0;
   bool safe_panel = false;       // Cholesky panels as two launches (GPSAT_SAFE_PANEL=1, or after a flag-wait timeout)
+  int la_max_nsr = LA_MAX_NSR;   // look-ahead panels for rounds of at most this many supertile rows (GPSAT_PANEL_LA)
   int* timeouts_dev = nullptr;   // [1] flag-wait timeouts of k_potrf_panel (device counter, see GPSAT_ESYNC)
   long long timeouts_seen = 0;   // value already reported to the caller
 };
@@ -119,9 +128,13 @@ extern "C" int gpsat_create(gpsat_handle** out, int device, size_t mem_budget_by
   gpsat_handle* h = new gpsat_handle();
   h->device = device;
   h->n_sm = prop.multiProcessorCount;
-  if (const char* eg = getenv("GPSAT_GROUPS")) h->n_groups = std::max(1, std::min(MAX_GROUPS, atoi(eg)));
+  if (const char* eg = getenv("GPSAT_GROUPS")) {
+    h->n_groups = std::max(1, std::min(MAX_GROUPS, atoi(eg)));
+    h->n_groups_env = true;
+  }
   if (const char* es = getenv("GPSAT_MAX_SLOTS")) h->max_slots = std::max(1, atoi(es));
   if (const char* sp = getenv("GPSAT_SAFE_PANEL")) h->safe_panel = atoi(sp) != 0;
+  if (const char* la = getenv("GPSAT_PANEL_LA")) h->la_max_nsr = std::max(0, atoi(la));   // 0: never
   size_t free_b = 0, total_b = 0;
   CK(cudaMemGetInfo(&free_b, &total_b));
   h->budget = mem_budget_bytes ? mem_budget_bytes : (size_t)(0.7 * (double)free_b);
@@ -362,17 +375,28 @@ static int run_round_flags(gpsat_handle* h, const SlotCtx& c, int nbm, int flags
     ++h->launches;
   }
   if (prof) cudaEventRecord(next_event(h), st);
-  for (int J = 0; J < nsr; ++J) {
-    const int n_off = c.S * (nsr - J - 1);
-    if (!h->safe_panel) {
-      k_potrf_panel<<<c.S + n_off, NTHREADS, PANEL_SMEM_BYTES, st>>>(c, J, nsr, 0);
+  if (!h->safe_panel && nsr >= 2 && nsr <= h->la_max_nsr) {
+    // look-ahead mode (small matrices): panel 0's diagonal blocks, then one launch per panel J holding its
+    // off-diagonal blocks, whose row J + 1 CTAs go on to factorise the diagonal block of panel J + 1 (gpr2.cuh)
+    k_potrf_panel<<<c.S, NTHREADS, PANEL_SMEM_BYTES, st>>>(c, 0, nsr, 0, 0);
+    ++h->launches;
+    for (int J = 0; J + 1 < nsr; ++J) {
+      k_potrf_panel<<<c.S * (nsr - J - 1), NTHREADS, PANEL_SMEM_BYTES, st>>>(c, J, nsr, c.S, 1);
       ++h->launches;
-    } else {      // diagonal blocks complete (kernel boundary) before any block that waits for their flag starts
-      k_potrf_panel<<<c.S, NTHREADS, PANEL_SMEM_BYTES, st>>>(c, J, nsr, 0);
-      ++h->launches;
-      if (n_off > 0) {
-        k_potrf_panel<<<n_off, NTHREADS, PANEL_SMEM_BYTES, st>>>(c, J, nsr, c.S);
+    }
+  } else {
+    for (int J = 0; J < nsr; ++J) {
+      const int n_off = c.S * (nsr - J - 1);
+      if (!h->safe_panel) {
+        k_potrf_panel<<<c.S + n_off, NTHREADS, PANEL_SMEM_BYTES, st>>>(c, J, nsr, 0, 0);
         ++h->launches;
+      } else {      // diagonal blocks complete (kernel boundary) before any block that waits for their flag starts
+        k_potrf_panel<<<c.S, NTHREADS, PANEL_SMEM_BYTES, st>>>(c, J, nsr, 0, 0);
+        ++h->launches;
+        if (n_off > 0) {
+          k_potrf_panel<<<n_off, NTHREADS, PANEL_SMEM_BYTES, st>>>(c, J, nsr, c.S, 0);
+          ++h->launches;
+        }
       }
     }
   }
@@ -528,7 +552,10 @@ extern "C" int gpsat_gpr_optimise(gpsat_handle* h, const gpsat_batch* b, const d
   // latency-bound stretch (diagonal-block factorisations, launch tails, the optimiser step, the host's
   // look at the slot table) the other groups' CTAs fill the idle SMs.  Phase profiling keeps one group
   // so that the event timings are not overlapped.
-  int G = (h->profiling || S < 2 * MIN_GROUP_SLOTS) ? 1 : std::min(h->n_groups, S / MIN_GROUP_SLOTS);
+  // (small matrices run the look-ahead panels, which keep gaining from more groups: see LA_MAX_NSR)
+  const bool la_batch = !h->safe_panel && (pl.nbmax + 1) / 2 <= h->la_max_nsr;
+  const int want_groups = (la_batch && !h->n_groups_env) ? LA_GROUPS : h->n_groups;
+  int G = (h->profiling || S < 2 * MIN_GROUP_SLOTS) ? 1 : std::min(want_groups, S / MIN_GROUP_SLOTS);
   G = std::max(1, std::min(G, MAX_GROUPS));
   r = ensure_groups(h, G, S);
   if (r) return r;
@@ -1112,14 +1139,25 @@ extern "C" int gpsat_microbench(int device, int which, int param, int nk, double
     k_elem_accuracy<<<nsm * 8, 256>>>(param, std::max(1, nk), (unsigned long long*)buf);
     CK(cudaGetLastError());
     CK(cudaMemcpy(tflops_out, buf, 8, cudaMemcpyDeviceToHost));
-  } else if (which == 30) {   // microseconds per 128x128 diagonal block (one CTA per SM, nk repetitions)
-    CK(cudaMalloc(&buf, (size_t)nsm * (6 * TILE_BYTES + 64)));
-    CK(cudaMemset(buf, 0, (size_t)nsm * (6 * TILE_BYTES + 64)));
+  } else if (which == 30 || which == 31) {
+    // 30: microseconds per 128x128 diagonal block (one CTA per SM, nk repetitions)
+    // 31: SM cycles from the entry of diag_block_128 to its stage `param` (1..9, see ClockProbe), last repetition
+    CK(cudaMalloc(&buf, (size_t)nsm * (6 * TILE_BYTES + 64) + 256));
+    CK(cudaMemset(buf, 0, (size_t)nsm * (6 * TILE_BYTES + 64) + 256));
     double* ld = buf + (size_t)nsm * 6 * TILE_ELEMS;
     int* fl = (int*)(ld + 2 * nsm);
+    long long* stamps = (long long*)(buf + (size_t)nsm * (6 * TILE_ELEMS + 8));
     CK(cudaFuncSetAttribute(k_diag_bench, cudaFuncAttributeMaxDynamicSharedMemorySize, PANEL_SMEM_BYTES));
-    r = time_launch([&] { k_diag_bench<<<nsm, NTHREADS, PANEL_SMEM_BYTES>>>(nk, buf, fl, ld); }, &ms);
-    *tflops_out = ms * 1e3 / nk;
+    r = time_launch([&] {
+      k_diag_bench<<<nsm, NTHREADS, PANEL_SMEM_BYTES>>>(nk, buf, fl, ld, which == 31 ? stamps : nullptr);
+    }, &ms);
+    if (which == 30) {
+      *tflops_out = ms * 1e3 / nk;
+    } else {
+      long long st[16];
+      CK(cudaMemcpy(st, stamps, sizeof(st), cudaMemcpyDeviceToHost));
+      *tflops_out = (double)(st[std::max(0, std::min(15, param))] - st[0]);
+    }
   } else if (which == 20 || which == 21) {
     CK(cudaMalloc(&buf, 64));
     const int grid = nsm * 4;

@@ -178,7 +178,14 @@ __device__ __forceinline__ void chol8_inv(double* blk, double* invblk, double* d
   if (bad && lane == 0) *fail_flag = 1;
 }
 
-__device__ __forceinline__ void potf2_trtri_64(double* a, double* inv, double* dg, int g0, int N, int* fail_flag) {
+// stage probe of the diagonal-block routines: a no-op in the production kernels; the micro-benchmark (microbench.cuh)
+// passes one that records clock64() per stage
+struct NoProbe {
+  __device__ __forceinline__ void operator()(int) const {}
+};
+template <class PROBE = NoProbe>
+__device__ __forceinline__ void potf2_trtri_64(double* a, double* inv, double* dg, int g0, int N, int* fail_flag,
+                                               PROBE probe = PROBE(), int stage0 = 0) {
   const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5, q = lane >> 2, r = lane & 3;
   for (int t = tid; t < TB * LDI; t += NTHREADS) inv[t] = 0.0;
   __syncthreads();
@@ -219,6 +226,7 @@ __device__ __forceinline__ void potf2_trtri_64(double* a, double* inv, double* d
     }
     __syncthreads();   // block column jb of L is final
   }
+  probe(stage0);
   // triangular inverse: warp w sweeps block column w
   for (int ib = w + 1; ib < 8; ++ib) {
     double t0 = 0.0, t1 = 0.0;
@@ -244,6 +252,7 @@ __device__ __forceinline__ void potf2_trtri_64(double* a, double* inv, double* d
     __syncwarp();
   }
   __syncthreads();
+  probe(stage0 + 1);
 }
 
 // write L (from a/dg) and X (from inv) of a factorised diagonal block: L -> gL, X -> gX and sX (all swizzled)
@@ -279,19 +288,22 @@ constexpr int DIAG_P0 = DIAG_INV + TB * LDI;
 constexpr int DIAG_P1 = DIAG_P0 + TILE_ELEMS;
 constexpr int DIAG_P2 = DIAG_P1 + TILE_ELEMS;
 constexpr int DIAG_P3 = DIAG_P2 + TILE_ELEMS;
+template <class PROBE = NoProbe>
 __device__ __forceinline__ void diag_block_128(double* ws, double* dg, bool two, int j0, int N, int* fail_flag,
                                                double* gL00, double* gL10, double* gL11, double* gX00, double* gX10,
-                                               double* gX11, double* ld) {
+                                               double* gX11, double* ld, PROBE probe = PROBE()) {
   double* a = ws;
   double* inv = ws + DIAG_INV;
   double* P0 = ws + DIAG_P0;      // X00
   double* P1 = ws + DIAG_P1;      // C10, later M = L10 X00
   double* P2 = ws + DIAG_P2;      // C11, later X11
   double* P3 = ws + DIAG_P3;      // L10
-  potf2_trtri_64(a, inv, dg, j0 * TB, N, fail_flag);
+  probe(0);
+  potf2_trtri_64(a, inv, dg, j0 * TB, N, fail_flag, probe, 1);
   emit_diag(a, inv, dg, gL00, gX00, P0);
   emit_logdet(dg, j0 * TB, N, ld);
   __syncthreads();
+  probe(3);
   if (!two) return;
   const int j1 = j0 + 1;
   FragCoord fc;
@@ -303,6 +315,7 @@ __device__ __forceinline__ void diag_block_128(double* ws, double* dg, bool two,
     store_acc_swizzled(gL10, t, fc);
   }
   __syncthreads();
+  probe(4);
   {  // C11' = C11 - L10 L10'
     Acc t;
     t.zero();
@@ -317,10 +330,11 @@ __device__ __forceinline__ void diag_block_128(double* ws, double* dg, bool two,
           a[m * LDA + n] = P2[swz(m, n)] - t.c[mi][ni][e];
         }
   }
-  potf2_trtri_64(a, inv, dg, j1 * TB, N, fail_flag);
+  potf2_trtri_64(a, inv, dg, j1 * TB, N, fail_flag, probe, 5);   // (its leading barrier closes stage 4 -> C11')
   emit_diag(a, inv, dg, gL11, gX11, P2);
   emit_logdet(dg, j1 * TB, N, ld + 1);
   __syncthreads();
+  probe(7);
   {  // M = L10 X00
     Acc t;
     t.zero();
@@ -328,12 +342,14 @@ __device__ __forceinline__ void diag_block_128(double* ws, double* dg, bool two,
     store_acc_swizzled(P1, t, fc);
   }
   __syncthreads();
+  probe(8);
   {  // X10 = -X11 M
     Acc t;
     t.zero();
     mma_tile<false, true>(t, P2, P1, fc);
     store_acc_swizzled(gX10, t, fc, -1.0);
   }
+  probe(9);
 }
 
 // ------------------------------------------------------------------------------------
@@ -366,7 +382,15 @@ __device__ __forceinline__ void st_release_gpu(int* p, int v) {
 // (block0 = 0); the safe mode of the host (api.cu: after a flag-wait timeout, or GPSAT_SAFE_PANEL=1) launches the
 // diagonal blocks [0, S) and the off-diagonal blocks [S, ...) as two kernels, so that the flag is set before any waiter
 // exists and nothing depends on the order in which the hardware dispatches CTAs.
-__global__ void __launch_bounds__(NTHREADS, 1) k_potrf_panel(SlotCtx c, int J, int nsr_max, int block0) {
+//
+// la = 1, LOOK-AHEAD mode (api.cu: small matrices): the launch holds the off-diagonal blocks of panel J only
+// (block0 = S), numbered with row I = J + 1 of every slot first.  That CTA owns ALL of row J + 1 of the factor once its
+// own L_{J+1, panel J} is written, so it carries on as the diagonal CTA of panel J + 1 (update over k < 2J + 2,
+// factorisation, flag = J + 2) inside the same launch: the diagonal block of every panel is published a whole launch
+// before its consumers exist, no CTA ever spins on a flag while holding an SM, and panel J + 1's 41 us serial
+// factorisation overlaps panel J's remaining off-diagonal CTAs.  Panel 0's diagonal blocks are their own launch
+// (block0 = 0, S blocks, la = 0).  Same arithmetic in the same order: results are bit-identical to the fused launch.
+__global__ void __launch_bounds__(NTHREADS, 1) k_potrf_panel(SlotCtx c, int J, int nsr_max, int block0, int la) {
   extern __shared__ __align__(128) double smem[];
   __shared__ __align__(8) uint64_t xbar[2];
   int s, I;
@@ -374,6 +398,15 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_potrf_panel(SlotCtx c, int J, i
   if (bid < c.S) {
     s = bid;
     I = J;
+  } else if (la) {
+    const int b = bid - c.S, nd = nsr_max - J - 1;
+    if (b < c.S) {               // the look-ahead CTAs (row J + 1) first: they are the long ones
+      s = b;
+      I = J + 1;
+    } else {
+      s = (b - c.S) / (nd - 1);
+      I = J + 2 + (b - c.S) % (nd - 1);
+    }
   } else {
     const int b = bid - c.S, nd = nsr_max - J - 1;
     s = b / nd;
@@ -382,12 +415,13 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_potrf_panel(SlotCtx c, int J, i
   // the three words of slot state are fetched together: one L2 round trip instead of three before the first copy
   const int act = c.active[s], nb = c.nb[s], N = c.n[s];
   if (!act) return;
-  const int j0 = 2 * J, j1 = 2 * J + 1;
+  int Jc = J;                                 // the panel this CTA is working on (J, then J + 1 in look-ahead mode)
+  int j0 = 2 * J, j1 = 2 * J + 1;
   if (2 * I >= nb) return;
   double* Lt = c.Lt + (long)s * c.tile_stride;
   double* Kt = c.Kt + (long)s * c.tile_stride;
   double* Xt = c.Xt + (long)s * c.tile_stride;
-  const bool two = (j1 < nb);
+  bool two = (j1 < nb);
   G2Pipe pipe;
   if (threadIdx.x == 0) {
     mbar_init(xbar, 1);
@@ -400,7 +434,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_potrf_panel(SlotCtx c, int J, i
     const int a = 2 * I + e, b = j0 + t;
     return (a < nb && b < nb && b <= a) ? tile_ptr(Kt, a, b) : nullptr;
   };
-  if (I != J) {
+  if (I != Jc) {
     // ---- off-diagonal supertile: C = K - sum_k L_Ik L_Jk', then L_I,panel = C X_JJ' ----
     // (rows 32-63 of the last tile row are skipped when they are all padding: their C and L entries are exact zeros)
     Frag2H f(2 * I, nb - 1, (N - (nb - 1) * TB) < 32);
@@ -413,7 +447,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_potrf_panel(SlotCtx c, int J, i
     const double* xe_src = two ? tile_ptr(Xt, j1, j1) : tile_ptr(Xt, j0, j0);
     bool xe_issued = false;
     // (thread 32 owns the X_JJ fetches, so that thread 0 goes straight to the first ring copies)
-    if (threadIdx.x == 32 && ld_acquire_gpu(c.pflag + s) == J + 1) {   // already published: the common case
+    // (the flag only grows within an evaluation -- a look-ahead CTA may already have published panel J + 1 -- hence >=)
+    if (threadIdx.x == 32 && ld_acquire_gpu(c.pflag + s) >= J + 1) {   // already published: the common case
       fence_proxy_async_all();
       mbar_expect_tx(xbar, TILE_BYTES);
       bulk_g2s(sXe, xe_src, TILE_BYTES, xbar);
@@ -442,7 +477,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_potrf_panel(SlotCtx c, int J, i
       // the time this one runs and the wait is short.  It is bounded anyway (~1 s): a lost flag marks the slot
       // as failed (objective = +inf) and is reported to the caller as GPSAT_ESYNC instead of hanging the device.
       int spins = 0;
-      while (ld_acquire_gpu(c.pflag + s) != J + 1) {
+      while (ld_acquire_gpu(c.pflag + s) < J + 1) {
         __nanosleep(200);
         if (++spins > 4000000) {
           c.fail[s] = 1;                                  // the evaluation is unusable: f = +inf for this slot ...
@@ -480,7 +515,17 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_potrf_panel(SlotCtx c, int J, i
       }
     }
     if (ti < nb && tj < nb) store_acc2(tile_ptr(Lt, ti, tj), acc, f);
-    return;
+    if (!(la && I == J + 1)) return;
+    // ---- look-ahead: this CTA now holds every tile of row J + 1 of the factor; become the diagonal CTA of panel J + 1.
+    // Its own stores of L_{J+1, panel J} are read back by TMA below: gpu-scope fence for the global writes, proxy fence
+    // generic -> async for them and for the shared memory the ring is about to overwrite, then the block barrier.
+    __threadfence();
+    fence_proxy_async_all();
+    __syncthreads();
+    Jc = J + 1;
+    j0 = 2 * Jc;
+    j1 = j0 + 1;
+    two = (j1 < nb);
   }
   // ---- diagonal 128x128 block: update of the three lower tiles with the balanced diagonal warp map (gemm2.cuh:
   //      a k-step costs 3/4 of a full supertile's), then the in-CTA factorisation ----
@@ -526,7 +571,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_potrf_panel(SlotCtx c, int J, i
   // publish: every thread's global stores -> gpu scope, then one release store of the flag
   __threadfence();
   __syncthreads();
-  if (threadIdx.x == 0) st_release_gpu(c.pflag + s, J + 1);
+  if (threadIdx.x == 0) st_release_gpu(c.pflag + s, Jc + 1);
 }
 
 // a'a from the augmented row of the factor (must run before k_trtri_* recycles Lt).  grid (S)

@@ -101,7 +101,17 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_gemm2_bench(const double* tiles
 
 // the 128x128 diagonal-block routine of the Cholesky panels in isolation: every CTA factorises `reps` times a
 // diagonally dominant block it builds in shared memory; out[0..] receives scratch tiles
-__global__ void __launch_bounds__(NTHREADS, 1) k_diag_bench(int reps, double* scratch, int* fail, double* ld) {
+// stage stamps of diag_block_128 (block 0, thread 0, last repetition): 0 entry | 1 64x64 factor of block 0 | 2 its
+// inverse sweep | 3 L00/X00 written | 4 L10 = C10 X00' | 5 C11 - L10 L10' + 64x64 factor of block 1 | 6 its inverse sweep |
+// 7 L11/X11 written | 8 M = L10 X00 | 9 X10 = -X11 M issued
+struct ClockProbe {
+  long long* out;
+  __device__ __forceinline__ void operator()(int stage) const {
+    if (out && blockIdx.x == 0 && threadIdx.x == 0) out[stage] = clock64();
+  }
+};
+__global__ void __launch_bounds__(NTHREADS, 1) k_diag_bench(int reps, double* scratch, int* fail, double* ld,
+                                                            long long* stamps) {
   extern __shared__ __align__(128) double smem[];
   double* dg = smem + G2_SMEM_ELEMS + TILE_ELEMS;
   double* g = scratch + (long)blockIdx.x * 6 * TILE_ELEMS;
@@ -116,7 +126,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_diag_bench(int reps, double* sc
     }
     __syncthreads();
     diag_block_128(smem, dg, true, 0, 1 << 30, fail + blockIdx.x, g, g + TILE_ELEMS, g + 2 * TILE_ELEMS,
-                   g + 3 * TILE_ELEMS, g + 4 * TILE_ELEMS, g + 5 * TILE_ELEMS, ld + 2 * blockIdx.x);
+                   g + 3 * TILE_ELEMS, g + 4 * TILE_ELEMS, g + 5 * TILE_ELEMS, ld + 2 * blockIdx.x, ClockProbe{stamps});
   }
 }
 

@@ -633,3 +633,36 @@ def test_safe_panel_mode_is_bitwise_equivalent(eng):
     np.testing.assert_array_equal(out["0"][1], out["1"][1])
     assert out["1"][2] > out["0"][2]          # the safe mode really took the two-launch path
     assert eng.sync_timeouts() == 0
+
+
+def test_lookahead_panel_mode_is_bitwise_equivalent(eng):
+    """Look-ahead Cholesky panels (GPSAT_PANEL_LA = largest number of supertile rows it is used for; default: small
+    matrices only): the row-(J+1) CTA of panel J's launch goes on to factorise the diagonal block of panel J+1, so no CTA
+    ever waits for a flag.  Same arithmetic in the same order as the fused one-launch-per-panel mode: objective and
+    gradient are bit-identical, for mixed sizes (slots whose last panel comes early), with and without a second tile
+    row in the last supertile row, and no flag wait ever times out."""
+    from gpsat_b200.engine import Engine
+    rng = np.random.default_rng(11)
+    sizes = [1500, 700, 130, 64, 63, 300, 513, 1025, 128, 127, 641]
+    Xs, zs = [], []
+    for n in sizes:
+        X, z, cs = _synth(rng, n)
+        Xs.append(X)
+        zs.append(z)
+    off, Xc, zc = _pack(Xs, zs)
+    theta = np.array([3.0, 2.5, 4.0, 0.02, 0.004])
+    out = {}
+    for mode in ("0", "99"):
+        os.environ["GPSAT_PANEL_LA"] = mode
+        e2 = Engine(0)
+        try:
+            b = e2.make_batch(off, Xc, zc, coords_scale=cs)
+            f, g = e2.eval(b, theta, grad=True)
+            out[mode] = (f.cpu().numpy(), g.cpu().numpy())
+            assert e2.sync_timeouts() == 0
+        finally:
+            e2.close()
+            os.environ.pop("GPSAT_PANEL_LA", None)
+    assert np.isfinite(out["0"][0]).all()
+    np.testing.assert_array_equal(out["0"][0], out["99"][0])
+    np.testing.assert_array_equal(out["0"][1], out["99"][1])
