@@ -110,6 +110,9 @@ _EXPORTS = {
     "gpsat_bin_accumulate": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_longlong, C.c_void_p, C.c_int,
                                        C.c_double, C.c_int, C.c_void_p, C.c_int, C.c_double, C.c_int, C.c_int,
                                        C.c_void_p, C.c_void_p, C.c_void_p]),
+    "gpsat_bin_spread": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_longlong, C.c_void_p, C.c_int,
+                                   C.c_double, C.c_int, C.c_void_p, C.c_int, C.c_double, C.c_int, C.c_int,
+                                   C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "gpsat_dmma_peak": (C.c_int, [C.c_int, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
     "gpsat_microbench": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_double)]),
     "gpsat_lbfgs_state_bytes": (C.c_size_t, []),

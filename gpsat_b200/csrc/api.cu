@@ -1239,6 +1239,26 @@ extern "C" int gpsat_bin_accumulate(const double* x_dev, const double* y_dev, co
   return 0;
 }
 
+extern "C" int gpsat_bin_spread(const double* x_dev, const double* y_dev, const double* vals_dev, const int* group_dev,
+                                long long n, const double* x_edges_dev, int n_x_edges, double x_round_scale,
+                                int x_round_div, const double* y_edges_dev, int n_y_edges, double y_round_scale,
+                                int y_round_div, int n_groups, const double* sum_dev,
+                                const unsigned long long* count_dev, double* ssd_dev, double* min_dev, double* max_dev,
+                                void* stream) {
+  if (!x_dev || !vals_dev || !x_edges_dev || n_x_edges < 2 || n_groups < 1 || (y_dev && (!y_edges_dev || n_y_edges < 2)) ||
+      (ssd_dev && (!sum_dev || !count_dev)) || (!ssd_dev && !min_dev && !max_dev))
+    return fail(GPSAT_EINVAL, "bad argument");
+  if (n <= 0) return 0;
+  BinAxis ax{x_edges_dev, n_x_edges, x_round_scale, x_round_div};
+  BinAxis ay{y_edges_dev, n_y_edges, y_round_scale, y_round_div};
+  const long long want = (n + 255) / 256;
+  const unsigned grid = (unsigned)std::min<long long>(want, 148LL * 16);
+  k_bin_spread<<<grid, 256, 0, (cudaStream_t)stream>>>(x_dev, y_dev, vals_dev, group_dev, n, ax, ay, y_dev != nullptr,
+                                                     sum_dev, count_dev, ssd_dev, min_dev, max_dev);
+  CK(cudaGetLastError());
+  return 0;
+}
+
 // ---- host-side L-BFGS hooks (same code the device runs) ----
 extern "C" size_t gpsat_lbfgs_state_bytes(void) { return sizeof(LbfgsState); }
 extern "C" void gpsat_lbfgs_init_host(void* state, const double* x0, int n) {

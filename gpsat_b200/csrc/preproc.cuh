@@ -4,6 +4,9 @@
 //                      in ONE launch: bin numbers exactly as scipy's binned_statistic_dd assigns them
 //                      (searchsorted(edges, v, side="right"), values that round onto the last edge go into the last
 //                      bin), then fp64 atomic sums and integer counts per (group, x bin, y bin).
+//   k_bin_spread       second pass for statistic = "std" | "min" | "max": with the per-bin sums and counts of the first
+//                      pass known, accumulates sum (v - mean_bin)^2 (np.std's two-pass form, which is what scipy applies
+//                      per bin) and the per-bin extrema (compare-and-swap on the fp64 bit pattern).
 // HBM-bound scatter-reduce: 24-28 bytes read per observation, atomics resolved in L2.
 #pragma once
 #include "common.cuh"
@@ -53,6 +56,55 @@ __global__ void __launch_bounds__(256) k_bin_accumulate(const double* __restrict
     const long long b = (g * nx + (bx - 1)) * ny + (by - 1);
     atomicAdd(sum + b, vals[i]);
     atomicAdd(cnt + b, 1ULL);
+  }
+}
+
+__device__ __forceinline__ void atomic_min_f64(double* addr, double v) {
+  unsigned long long* a = reinterpret_cast<unsigned long long*>(addr);
+  unsigned long long old = *reinterpret_cast<volatile unsigned long long*>(a);
+  while (v < __longlong_as_double((long long)old)) {
+    const unsigned long long seen = atomicCAS(a, old, (unsigned long long)__double_as_longlong(v));
+    if (seen == old) break;
+    old = seen;
+  }
+}
+__device__ __forceinline__ void atomic_max_f64(double* addr, double v) {
+  unsigned long long* a = reinterpret_cast<unsigned long long*>(addr);
+  unsigned long long old = *reinterpret_cast<volatile unsigned long long*>(a);
+  while (v > __longlong_as_double((long long)old)) {
+    const unsigned long long seen = atomicCAS(a, old, (unsigned long long)__double_as_longlong(v));
+    if (seen == old) break;
+    old = seen;
+  }
+}
+
+// same row -> bin map as k_bin_accumulate.  sum / cnt: the first pass.  ssd, vmin, vmax: [n_groups][nx][ny] or nullptr
+// (ssd zeroed, vmin = +inf, vmax = -inf by the caller).
+__global__ void __launch_bounds__(256) k_bin_spread(const double* __restrict__ x, const double* __restrict__ y,
+                                                    const double* __restrict__ vals, const int* __restrict__ group,
+                                                    long long n, BinAxis ax, BinAxis ay, int two_d,
+                                                    const double* __restrict__ sum,
+                                                    const unsigned long long* __restrict__ cnt,
+                                                    double* __restrict__ ssd, double* __restrict__ vmin,
+                                                    double* __restrict__ vmax) {
+  const int nx = ax.n_edges - 1, ny = two_d ? ay.n_edges - 1 : 1;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const int bx = bin_number(ax, x[i]);
+    if (bx < 1 || bx > nx) continue;
+    int by = 1;
+    if (two_d) {
+      by = bin_number(ay, y[i]);
+      if (by < 1 || by > ny) continue;
+    }
+    const long long g = group ? group[i] : 0;
+    const long long b = (g * nx + (bx - 1)) * ny + (by - 1);
+    const double v = vals[i];
+    if (ssd) {
+      const double d = v - __ddiv_rn(sum[b], (double)cnt[b]);
+      atomicAdd(ssd + b, __dmul_rn(d, d));
+    }
+    if (vmin) atomic_min_f64(vmin + b, v);
+    if (vmax) atomic_max_f64(vmax + b, v);
   }
 }
 

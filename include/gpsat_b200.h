@@ -255,6 +255,17 @@ int gpsat_bin_accumulate(const double* x_dev, const double* y_dev, const double*
                          const double* y_edges_dev, int n_y_edges, double y_round_scale, int y_round_div,
                          int n_groups, double* sum_dev, unsigned long long* count_dev, void* stream);
 
+/* Second pass over the same rows for scipy's statistic = "std" | "min" | "max" (GPSat/dataprepper.py:359 as called
+ * with bin_statistic=["mean", "std", "count"] in examples/bin_data.py:165): with sum_dev / count_dev of
+ * gpsat_bin_accumulate, ssd_dev (zeroed by the caller) receives the per-bin sum of (v - mean)^2 -- np.std's two-pass
+ * form, std = sqrt(ssd / count) -- and min_dev / max_dev (initialised to +inf / -inf) the per-bin extrema.  Any of the
+ * three outputs may be NULL; sum_dev / count_dev are needed only with ssd_dev.  Same row -> bin map as the first pass. */
+int gpsat_bin_spread(const double* x_dev, const double* y_dev, const double* vals_dev, const int* group_dev,
+                     long long n, const double* x_edges_dev, int n_x_edges, double x_round_scale, int x_round_div,
+                     const double* y_edges_dev, int n_y_edges, double y_round_scale, int y_round_div, int n_groups,
+                     const double* sum_dev, const unsigned long long* count_dev, double* ssd_dev, double* min_dev,
+                     double* max_dev, void* stream);
+
 /* roofline denominator for the factorisation kernels: FP64 mma.sync (DMMA m8n8k4) issue rate of
  * this GPU measured with register-resident accumulator chains (no memory traffic). */
 int gpsat_dmma_peak(int device, int iters, double* tflops_out, double* ms_out);

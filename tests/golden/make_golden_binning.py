@@ -29,7 +29,7 @@ def main():
     z = rng.normal(0.3, 0.1, n)
     df = pd.DataFrame({"x": x, "y": y, "z": z})
     out = dict(x=x, y=y, z=z, x_range=np.array([-1.0e6, 1.0e6]), y_range=np.array([-1.0e6, 1.0e6]), grid_res=50_000.0)
-    for st in ("mean", "count", "sum"):
+    for st in ("mean", "count", "sum", "std", "min", "max"):
         b, (xc, yc) = DataPrep.bin_data(df, x_range=[-1.0e6, 1.0e6], y_range=[-1.0e6, 1.0e6], grid_res=50_000.0,
                                         x_col="x", y_col="y", val_col="z", bin_statistic=st)
         out[f"b2_{st}"] = b

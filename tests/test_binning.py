@@ -18,7 +18,7 @@ def _frame():
 
 def test_oracle_bin_data_matches_reference():
     df = _frame()
-    for st in ("mean", "count", "sum"):
+    for st in ("mean", "count", "sum", "std", "min", "max"):
         b, (xc, yc) = ob.bin_data(df, XR, YR, RES, val_col="z", bin_statistic=st)
         np.testing.assert_array_equal(b, G[f"b2_{st}"])
     np.testing.assert_array_equal(xc, G["xc"])
@@ -39,6 +39,13 @@ def test_gpu_bin_data_golden():
     np.testing.assert_allclose(b, G["b2_mean"], rtol=1e-12)
     b, _ = DataPrep.bin_data(df, x_range=XR, y_range=YR, grid_res=RES, val_col="z", bin_statistic="sum")
     np.testing.assert_allclose(b, G["b2_sum"], rtol=1e-12, atol=1e-13)
+    # second-pass statistics (examples/bin_data.py:165 bins ["mean", "std", "count"]): extrema exact, std to rounding
+    for st in ("min", "max"):
+        b, _ = DataPrep.bin_data(df, x_range=XR, y_range=YR, grid_res=RES, val_col="z", bin_statistic=st)
+        np.testing.assert_array_equal(b, G[f"b2_{st}"])                  # NaN in the same (empty) bins, same values
+    b, _ = DataPrep.bin_data(df, x_range=XR, y_range=YR, grid_res=RES, val_col="z", bin_statistic="std")
+    assert np.array_equal(np.isnan(b), np.isnan(G["b2_std"]))
+    np.testing.assert_allclose(b, G["b2_std"], rtol=1e-11, atol=1e-15)   # single-sample bins: exactly 0 in both
     b1, xc1 = DataPrep.bin_data(df, x_range=XR, grid_res=12_500.0, x_col="x", val_col="z", bin_2d=False)
     np.testing.assert_array_equal(xc1, G["xc1"])
     np.testing.assert_allclose(b1, G["b1_mean"], rtol=1e-12)
@@ -63,6 +70,15 @@ def test_gpu_bin_data_by_matches_oracle():
     assert out.index.names == ref.index.names and out.index.equals(ref.index)
     assert np.array_equal(np.isnan(out["z"].values), np.isnan(ref["z"].values))
     np.testing.assert_allclose(out["z"].values, ref["z"].values, rtol=1e-12)
+    # several statistics in one call, as examples/bin_data.py:165 asks for (one first pass, one second pass for std)
+    multi = DataPrep.bin_data_by(df, by_cols=["source", "date"], val_col="z", x_range=XR, y_range=YR, grid_res=RES,
+                                 bin_statistic=["mean", "std", "count", "max"])
+    assert list(multi.columns) == ["z_mean", "z_std", "z_count", "z_max"]
+    for st, tol in (("mean", 1e-12), ("std", 1e-10), ("count", 0.0), ("max", 0.0)):
+        r = ob.bin_data_by(df, ["source", "date"], "z", "x", "y", XR, YR, RES, bin_statistic=st)["z"].values
+        o = multi[f"z_{st}"].values
+        assert np.array_equal(np.isnan(o), np.isnan(r)), st
+        np.testing.assert_allclose(o, r, rtol=tol, atol=1e-15 if tol else 0.0, err_msg=st)
     # the usual follow-up (examples: .dropna().reset_index()) gives the observation table of the hot path
     obs = out.dropna().reset_index()
     assert set(obs.columns) == {"y", "x", "source", "date", "z"} and len(obs) > 1000
@@ -79,7 +95,7 @@ def test_gpu_binning_full_size_properties():
     y = rng.uniform(-4.6e6, 4.6e6, n)
     z = rng.normal(0.3, 0.1, n)
     xe, ye = dp._edges([-4.5e6, 4.5e6], [-4.5e6, 4.5e6], 5_000.0, True)
-    s, c = dp._accumulate(x, y, z, None, 1, xe, ye)
+    s, c, _ = dp._accumulate(x, y, z, None, 1, xe, ye)
     inside = (x >= xe[0]) & (x <= xe[-1]) & (y >= ye[0]) & (y <= ye[-1])
     assert int(c.sum()) == int(inside.sum())
     np.testing.assert_allclose(s.sum(), z[inside].sum(), rtol=1e-11)
