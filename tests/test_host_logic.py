@@ -147,3 +147,57 @@ def test_register_wraps_get_model_in_all_three_namespaces():
                 sys.modules.pop(k, None)
             else:
                 sys.modules[k] = v
+
+
+def test_result_buffers_are_recycled_only_when_unreferenced():
+    """batched.to_host hands out views of one pageable buffer per call and reuses a buffer for the next call only when
+    nothing references it any more (views of views included); a caller that keeps any piece gets a fresh buffer."""
+    import numpy as np
+    from gpsat_b200 import batched as b
+    b._HOST_POOL.clear()
+    buf = b._host_buffer(4096)
+    a = buf[:800].view(np.float64)
+    piece = a[10:20]                      # a view of a view still pins the owner
+    a[:] = 7.0
+    del buf, a
+    other = b._host_buffer(1024)
+    assert not np.shares_memory(other, piece)            # still referenced: not handed out again
+    assert piece[0] == 7.0
+    del piece, other
+    again = b._host_buffer(2048)
+    assert any(again is x for x in b._HOST_POOL) and len(b._HOST_POOL) == 2      # one of the two idle buffers, reused
+    held = [again]
+    for _ in range(8):                    # a caller that keeps everything: the pool stays bounded
+        held.append(b._host_buffer(1 << 20))
+    assert len(b._HOST_POOL) <= b._HOST_POOL_MAX
+    held[1][:] = 3                        # forgotten by the pool, alive as long as the caller holds it
+    assert held[1][0] == 3
+    b._HOST_POOL.clear()
+
+
+def test_pinned_result_buffers_alternate_and_fall_back(monkeypatch):
+    """batched._pinned_buffer (the zero-copy path of to_host): at most two page-locked buffers, handed out only when
+    unreferenced; with both still held the caller is told to use the staging path (None)."""
+    import numpy as np
+    import torch
+    from gpsat_b200 import batched as b
+    real_empty = torch.empty
+    monkeypatch.setattr(torch, "empty", lambda *a, **k: real_empty(*a, **{x: y for x, y in k.items()
+                                                                          if x != "pin_memory"}))   # no CUDA here
+    b._PINNED_POOL.clear()
+    t1, r1 = b._pinned_buffer(1000)
+    first = r1[:80].view(np.float64)
+    del t1, r1
+    t2, r2 = b._pinned_buffer(1000)
+    assert not np.shares_memory(first, r2) and len(b._PINNED_POOL) == 2
+    second = r2[:8]
+    del t2, r2
+    assert b._pinned_buffer(100) is None                      # both referenced: fall back
+    del first
+    t3, r3 = b._pinned_buffer(500)
+    assert r3 is b._PINNED_POOL[0][1]                          # the released one is reused
+    del t3, r3
+    t4, r4 = b._pinned_buffer(100_000)                         # too small: the idle buffer is replaced, not added
+    assert len(b._PINNED_POOL) == 2 and r4.nbytes >= 100_000
+    del second, t4, r4
+    b._PINNED_POOL.clear()
