@@ -470,10 +470,13 @@ class LocalExpertOI:
             chunk = {}
             # tables in the order the reference's save_dict holds them (run_details, preds, parameters)
             for name, lst in sorted(pieces.items(), key=lambda kv: {"run_details": 0, "preds": 1}.get(kv[0], 2)):
-                df = pd.concat(lst, axis=0)
-                # rows back in the order the sequential loop would have appended them
-                df = df.iloc[np.argsort(df["_pos_"].values, kind="stable")].drop(columns="_pos_")
-                chunk[f"{name}{table_suffix}"] = df
+                df = lst[0] if len(lst) == 1 else pd.concat(lst, axis=0)
+                # rows back in the order the sequential loop would have appended them (one where-group per chunk, the
+                # usual case, is in that order already: no second pass over the prediction rows)
+                posv = df["_pos_"].values
+                if len(posv) > 1 and (posv[1:] < posv[:-1]).any():
+                    df = df.iloc[np.argsort(posv, kind="stable")]
+                chunk[f"{name}{table_suffix}"] = df.drop(columns="_pos_")
             if store_path is not None and is_writer:
                 self._flush(store_path, chunk)
             if return_tables:
@@ -601,10 +604,20 @@ class LocalExpertOI:
         coords_col = self.coords_col
         ref_all = sub[coords_col].values
 
-        def midx(rows_ref):
+        def midx(rows_ref, repeats=None):
+            """index of the expert coordinates, row e repeated repeats[e] times.  The levels are factorised over the
+            EXPERT rows and the codes repeated (MultiIndex.from_arrays over the repeated rows gives the same index but
+            factorises every level over millions of prediction rows: a third of the host time of a predict-only batch)"""
             if len(coords_col) == 1:
-                return pd.Index(rows_ref[:, 0], name=coords_col[0])
-            return pd.MultiIndex.from_arrays([rows_ref[:, j] for j in range(len(coords_col))], names=coords_col)
+                v = rows_ref[:, 0] if repeats is None else np.repeat(rows_ref[:, 0], repeats)
+                return pd.Index(v, name=coords_col[0])
+            levels, codes = [], []
+            for j in range(len(coords_col)):
+                cat = pd.Categorical(rows_ref[:, j])               # sorted unique levels, as from_arrays builds them
+                levels.append(cat.categories)
+                c = np.asarray(cat.codes)
+                codes.append(c if repeats is None else np.repeat(c, repeats))
+            return pd.MultiIndex(levels=levels, codes=codes, names=coords_col, verify_integrity=False)
 
         def details(r, num_obs, rt, fobj, succ, ran, ref, pp):
             return pd.DataFrame({"_dim_0": 0, "num_obs": num_obs[r], "run_time": rt[r],
@@ -652,7 +665,7 @@ class LocalExpertOI:
             if "lengthscales" in names:
                 pieces.setdefault("lengthscales", []).append(pd.DataFrame(
                     {"_dim_0": np.tile(np.arange(D), len(k)), "lengthscales": th[:, :D].ravel(),
-                     "_pos_": np.repeat(pp[k], D)}, index=midx(np.repeat(ref[k], D, axis=0))))
+                     "_pos_": np.repeat(pp[k], D)}, index=midx(ref[k], D)))
             if "kernel_variance" in names:
                 pieces.setdefault("kernel_variance", []).append(pd.DataFrame(
                     {"_dim_0": 0, "kernel_variance": th[:, D], "_pos_": pp[k]}, index=midx(ref[k])))
@@ -666,23 +679,45 @@ class LocalExpertOI:
                 d0 = np.concatenate([np.repeat(np.arange(m), D) for m in mk])
                 pieces.setdefault("inducing_points", []).append(pd.DataFrame(
                     {"_dim_0": d0, "_dim_1": np.tile(np.arange(D), len(rows)), "inducing_points": zc[rows].ravel(),
-                     "_pos_": np.repeat(pp[k], mk * D)}, index=midx(np.repeat(ref[k], mk * D, axis=0))))
+                     "_pos_": np.repeat(pp[k], mk * D)}, index=midx(ref[k], mk * D)))
         if predict:
+            # The prediction table is millions of rows for a predict-only batch: its float columns are gathered straight
+            # into ONE (columns x rows) block that the frame adopts without copying (a dict of column arrays is stacked
+            # and consolidated by pandas: two more passes over ~100 MB), and the rows of consecutive experts are a slice.
             poff = res["pred_offsets"]
             cntk = np.diff(poff)[vpos[k]]
-            sel = np.concatenate([np.arange(poff[v], poff[v + 1]) for v in vpos[k]])
-            dim0 = np.concatenate([np.arange(c) for c in cntk])
-            f_bar = np.repeat(res["obs_mean"][vpos[k]], cntk)
-            if self.model_config["init_params"].get("obs_mean", None) != "local":
+            starts = np.asarray(poff)[vpos[k]]
+            n_rows = int(cntk.sum())
+            first_row = np.cumsum(cntk) - cntk
+            dim0 = np.arange(n_rows) - np.repeat(first_row, cntk)
+            if np.array_equal(starts[1:], starts[:-1] + cntk[:-1]):
+                sl = slice(int(starts[0]), int(starts[0]) + n_rows)
+
+                def take(a, out):
+                    np.copyto(out, a[sl])
+            else:
+                sel = dim0 + np.repeat(starts, cntk)
+
+                def take(a, out):
+                    np.take(a, sel, out=out)
+            local_mean = self.model_config["init_params"].get("obs_mean", None) == "local"
+            fcols = ["f*", "f*_var", "y_var"] + (["f_bar"] if local_mean else []) + [f"pred_loc_{c}" for c in coords_col]
+            blk = np.empty((len(fcols), n_rows), dtype=np.float64)
+            take(res["fmean"], blk[0])
+            take(res["fvar"], blk[1])
+            take(res["yvar"], blk[2])
+            if local_mean:
+                blk[3] = np.repeat(res["obs_mean"][vpos[k]], cntk)
+            for ci in range(len(coords_col)):
+                take(res["pred_coords"][:, ci], blk[len(fcols) - len(coords_col) + ci])
+            pr = pd.DataFrame(blk.T, columns=fcols, index=midx(ref[k], cntk), copy=False)
+            pr.insert(0, "_dim_0", dim0)
+            if not local_mean:
                 # base_model.py:199-200: without obs_mean='local' the mean is the INTEGER array [[0]], and predict
                 # broadcasts it (gpflow_models.py:265-271): the stored column is int64 zeros, not float
-                f_bar = np.zeros(len(f_bar), dtype=np.int64)
-            pr = {"_dim_0": dim0, "f*": res["fmean"][sel], "f*_var": res["fvar"][sel], "y_var": res["yvar"][sel],
-                  "f_bar": f_bar}
-            for ci, c in enumerate(coords_col):
-                pr[f"pred_loc_{c}"] = res["pred_coords"][sel, ci]
+                pr.insert(4, "f_bar", np.zeros(n_rows, dtype=np.int64))
             pr["_pos_"] = np.repeat(pp[k], cntk)
-            pieces.setdefault("preds", []).append(pd.DataFrame(pr, index=midx(np.repeat(ref[k], cntk, axis=0))))
+            pieces.setdefault("preds", []).append(pr)
 
     @staticmethod
     def _flush(store_path, tables):
