@@ -151,13 +151,13 @@ def merge_shards(shard_idx: List[np.ndarray], parts: List[Dict[str, np.ndarray]]
         base = np.cumsum([0] + [int(p[offs_key][-1]) for p in live])[:-1]
         starts = np.concatenate([np.asarray(p[offs_key][:-1]) + b for p, b in zip(live, base)])
         cnt_o, starts_o = cnt[order], starts[order]
-        take = np.concatenate([np.arange(s, s + c) for s, c in zip(starts_o, cnt_o)]) if len(cnt_o) else \
-            np.zeros(0, dtype=np.int64)
         off = np.zeros(len(cnt_o) + 1, dtype=np.int64)
         off[1:] = np.cumsum(cnt_o)
+        # row r of the merged array comes from starts_o[e] + (r - off[e]) for the expert e that owns it
+        take = np.repeat(np.asarray(starts_o, dtype=np.int64) - off[:-1], cnt_o) + np.arange(off[-1], dtype=np.int64)
         out[offs_key] = off
         for k in keys:
-            out[k] = np.concatenate([p[k] for p in live])[take.astype(np.int64)]
+            out[k] = np.concatenate([p[k] for p in live])[take]
 
     if all("pred_offsets" in p for p in live):
         ragged("pred_offsets", PER_PRED)
