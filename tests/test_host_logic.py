@@ -201,3 +201,49 @@ def test_pinned_result_buffers_alternate_and_fall_back(monkeypatch):
     assert len(b._PINNED_POOL) == 2 and r4.nbytes >= 100_000
     del second, t4, r4
     b._PINNED_POOL.clear()
+
+
+def test_shape_tables_prediction_block_matches_per_expert_loop():
+    """LocalExpertOI._shape_tables gathers the prediction columns of a whole batch into one block (slice when the kept
+    experts' rows are consecutive, index map otherwise) and builds the MultiIndex from per-expert codes: same table as
+    the reference's per-expert dict_of_array_to_table loop (local_experts.py:691-747), for both row layouts and both
+    f_bar forms (float for obs_mean='local', int64 zeros otherwise, base_model.py:199-200)."""
+    import numpy as np
+    import pandas as pd
+    from gpsat_b200.local_experts import LocalExpertOI
+    rng = np.random.default_rng(3)
+    E, D = 7, 3
+    eloc = pd.DataFrame({"x": rng.integers(-3, 3, E) * 1e5, "y": rng.integers(-3, 3, E) * 1e5, "t": 18326.0})
+    cnt = np.array([4, 0, 6, 1, 3, 5, 2])
+    for local in (True, False):
+        for valid_idx in (np.arange(E), np.array([2, 0, 1, 6, 3, 5, 4])):        # consecutive rows / permuted rows
+            poff = np.r_[0, np.cumsum(cnt[valid_idx])]       # CSR over the VALID list, in valid_idx order
+            n = int(poff[-1])
+            res = dict(num_obs=rng.integers(5, 9, E), too_few=np.zeros(E, bool), valid_idx=valid_idx,
+                       fobj=rng.normal(size=E), status=np.ones(E, int), theta=rng.uniform(1, 2, (E, D + 2)),
+                       pred_offsets=poff, obs_mean=rng.normal(size=E), fmean=rng.normal(size=n),
+                       fvar=rng.uniform(size=n), yvar=rng.uniform(size=n), pred_coords=rng.normal(size=(n, D)))
+            oi = LocalExpertOI.__new__(LocalExpertOI)
+            oi.coords_col = ["x", "y", "t"]
+            oi.params_to_store = None
+            oi.model_config = {"init_params": {"obs_mean": "local"} if local else {}}
+            pieces = {}
+            oi._shape_tables(pieces, res, None, eloc, np.arange(E), np.ones(E, bool), 0.1, True, True, "m", "d", 1, D,
+                             True)
+            got = pieces["preds"][0]
+            rows = []
+            for e in range(E):                              # global expert order, one frame per expert
+                v = int(np.flatnonzero(valid_idx == e)[0])
+                sl = slice(poff[v], poff[v + 1])
+                c = poff[v + 1] - poff[v]
+                fb = np.full(c, res["obs_mean"][v]) if local else np.zeros(c, dtype=np.int64)
+                d = pd.DataFrame({"_dim_0": np.arange(c), "f*": res["fmean"][sl], "f*_var": res["fvar"][sl],
+                                  "y_var": res["yvar"][sl], "f_bar": fb,
+                                  "pred_loc_x": res["pred_coords"][sl, 0], "pred_loc_y": res["pred_coords"][sl, 1],
+                                  "pred_loc_t": res["pred_coords"][sl, 2], "_pos_": e},
+                                 index=pd.MultiIndex.from_arrays([np.full(c, eloc[k][e]) for k in "xyt"],
+                                                                 names=list("xyt")))
+                rows.append(d)
+            want = pd.concat(rows, axis=0)
+            pd.testing.assert_frame_equal(got, want, check_dtype=True)
+            assert got.index.equals(want.index) and list(got.index.names) == ["x", "y", "t"]
